@@ -1,0 +1,179 @@
+"""numpy-in / numpy-out entry points behind the reference-named modules.
+
+Each function stages its inputs through pinned host memory, launches the C-ABI sequence on
+the current CUDA stream and returns freshly allocated numpy arrays of the reference's dtype
+and layout.  All arithmetic happens in libf2cnn_b200.so."""
+import numpy as np
+import torch
+
+from . import engine
+
+_WAVE_DTYPES = (np.int16, np.float32, np.float64)
+
+
+def _as_wave(wave):
+    """The reference feeds scipy.signal.lfilter an int16 WAV array or a float64 noise-mixed
+    array (Evaluating.py:200); anything else is promoted to float64 like lfilter would."""
+    w = np.asarray(wave)
+    if w.ndim != 1:
+        raise ValueError("wave must be one-dimensional, got shape %s" % (w.shape,))
+    if w.dtype not in [np.dtype(d) for d in _WAVE_DTYPES]:
+        if w.dtype.kind in "iub" and w.dtype.itemsize <= 2:
+            w = w.astype(np.int16) if w.dtype != np.uint16 else w.astype(np.float64)
+        else:
+            w = w.astype(np.float64)
+    return np.ascontiguousarray(w)
+
+
+def _to_device(arr, device):
+    t = torch.from_numpy(arr)
+    if arr.nbytes >= (1 << 16):
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
+
+
+def _to_host(t):
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.numel() * t.element_size() >= (1 << 16))
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def erb_filterbank(wave, coefs):
+    """gammatone/filters.py:195-239 -> (C, n) float64."""
+    w = _as_wave(wave)
+    coefs = np.asarray(coefs, dtype=np.float64)
+    plan = engine.plan_for(coefs)
+    n = int(w.shape[0])
+    if n == 0:
+        return np.zeros((plan.n_channels, 0))
+    batch = plan.batch([n])
+    res = batch.run(_to_device(w, plan.device), gfb=torch.float64)
+    return _to_host(res["gfb"]).reshape(plan.n_channels, n)
+
+
+def filterbank_envelope(wave, coefs, LPF=False, CUTOFF=100, with_gfb=False, dtype=np.float64):
+    """Fused erb_filterbank + ExtractEnvelopeFromMatrix on one waveform: the (C,n) envelope
+    (and optionally the filterbank output) without the intermediate host round trip."""
+    w = _as_wave(wave)
+    coefs = np.asarray(coefs, dtype=np.float64)
+    plan = engine.plan_for(coefs)
+    n = int(w.shape[0])
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    if n == 0:
+        z = np.zeros((plan.n_channels, 0), dtype=dtype)
+        return (z, z.copy()) if with_gfb else z
+    batch = plan.batch([n])
+    res = batch.run(_to_device(w, plan.device), lpf=LPF, cutoff=CUTOFF, env=tdt, gfb=tdt if with_gfb else None)
+    env = _to_host(res["env"]).reshape(plan.n_channels, n)
+    if with_gfb:
+        return _to_host(res["gfb"]).reshape(plan.n_channels, n), env
+    return env
+
+
+def extract_envelope_from_matrix(matrix, LPF=False, CUTOFF=100):
+    """scripts/processing/EnvelopeExtraction.py:51-67 on an arbitrary (rows, n) matrix:
+    abs(paddedHilbert(row)) then lowPassFilter(row, CUTOFF) iff LPF -> float64, same shape."""
+    m = np.asarray(matrix)
+    if m.ndim != 2:
+        raise ValueError("matrix must be two-dimensional (channels x samples)")
+    if m.dtype not in (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int16)):
+        m = m.astype(np.float64)
+    m = np.ascontiguousarray(m)
+    rows, n = m.shape
+    if rows == 0:
+        return np.zeros(m.shape)
+    if n == 0:
+        # paddedHilbert(empty) -> scipy.signal.hilbert raises "N must be positive."
+        raise ValueError("N must be positive.")
+    plan = engine.any_plan()
+    out = plan.envelope_rows(_to_device(m, plan.device), LPF, CUTOFF, out_dtype=torch.float64)
+    return _to_host(out)
+
+
+def window_indices(n, centers, radius, step):
+    """Sample indices read by InputGenerator.py:76 for one file, with Python list
+    semantics: a negative index wraps once, anything else out of range is an IndexError."""
+    centers = np.asarray(centers, dtype=np.int64).reshape(-1)
+    offs = step * (np.arange(2 * radius + 1, dtype=np.int64) - radius)
+    idx = centers[:, None] + offs[None, :]
+    idx = np.where(idx < 0, idx + n, idx)
+    if idx.size and (idx.min() < 0 or idx.max() >= n):
+        raise IndexError("index out of bounds")
+    return idx
+
+
+def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=5, step=160, device_out=False):
+    """Fused path from waveforms to the (N, 2R+1, C) float32 input tensor.
+
+    waves: list of 1-D arrays (same dtype); timepoints: list of int arrays (window centres
+    per utterance, in output order).  Equivalent to erb_filterbank ->
+    ExtractEnvelopeFromMatrix(LPF, CUTOFF) -> the gather of InputGenerator.py:73-80 per
+    utterance, rows concatenated in list order."""
+    coefs = np.asarray(coefs, dtype=np.float64)
+    plan = engine.plan_for(coefs)
+    C = plan.n_channels
+    dots = 2 * radius + 1
+    waves = [_as_wave(w) for w in waves]
+    dts = {w.dtype for w in waves}
+    if len(dts) > 1:
+        waves = [w.astype(np.float64) for w in waves]
+    lengths = np.asarray([w.shape[0] for w in waves], dtype=np.int64)
+    idx = [window_indices(int(n), tp, radius, step) for n, tp in zip(lengths, timepoints)]
+    total = int(sum(i.shape[0] for i in idx))
+    if total == 0:
+        return np.zeros((0, dots, C), dtype=np.float32)
+    # one decimated grid serves every window when all indices share a residue mod step
+    allidx = np.concatenate([i.reshape(-1) for i in idx if i.size])
+    phase = int(allidx[0] % step)
+    on_grid = bool(np.all(allidx % step == phase))
+    flat = np.concatenate(waves) if len(waves) > 1 else waves[0]
+    wave_dev = _to_device(flat, plan.device)
+    if on_grid:
+        batch = plan.batch(lengths, step=step, phase=phase)
+        res = batch.run(wave_dev, lpf=LPF, cutoff=CUTOFF, dec=True)
+        bases, strided = [], True
+        for u, i in enumerate(idx):
+            if not i.size:
+                continue
+            rows = (i - phase) // step + batch.frame_offsets[u]
+            strided = strided and bool(np.all(np.diff(rows, axis=1) == 1))
+            bases.append(rows)
+        rows = np.concatenate(bases)
+        if strided:
+            base_dev = _to_device(np.ascontiguousarray(rows[:, 0]), plan.device)
+            out = engine.gather_windows(res["dec"], base_dev, dots, 1)
+        else:
+            out = engine.gather_index(res["dec"], _to_device(np.ascontiguousarray(rows.reshape(-1)), plan.device))
+            out = out.view(total, dots, C)
+    else:
+        batch = plan.batch(lengths, step=step, phase=0)
+        res = batch.run(wave_dev, lpf=LPF, cutoff=CUTOFF, env_t=True)
+        rows = np.concatenate([i + batch.sample_offsets[u] for u, i in enumerate(idx) if i.size])
+        out = engine.gather_index(res["env_t"], _to_device(np.ascontiguousarray(rows.reshape(-1)), plan.device))
+        out = out.view(total, dots, C)
+    return out if device_out else _to_host(out)
+
+
+def dense_frames(wave, coefs, LPF=False, CUTOFF=100, radius=5, step=160, normalize=True, dtype=np.float64,
+                 frames=None):
+    """In-memory front end of Evaluating.EvaluateOneWavArray (Evaluating.py:52-80):
+    filterbank -> envelope -> dense stride-1 framing (-> normalizeInput per frame).
+    Returns (nb, 2R+1, C); `frames=(i0, i1)` restricts the frame range."""
+    w = _as_wave(wave)
+    coefs = np.asarray(coefs, dtype=np.float64)
+    plan = engine.plan_for(coefs)
+    n = int(w.shape[0])
+    dots = 2 * radius + 1
+    nb = int(n - dots * step)
+    i0, i1 = (0, nb) if frames is None else frames
+    if nb <= 0 or i1 <= i0:
+        return np.zeros((0, dots, plan.n_channels), dtype=dtype)
+    batch = plan.batch([n], step=step)
+    res = batch.run(_to_device(w, plan.device), lpf=LPF, cutoff=CUTOFF, env_t=True)
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    out, flag = engine.dense_frames(res["env_t"], dots, step, i0, i1, normalize=normalize, out_dtype=tdt)
+    host = _to_host(out)
+    if normalize and int(flag.item()) != 0:
+        raise ValueError("values must all be positive")  # Training.py:18-20
+    return host

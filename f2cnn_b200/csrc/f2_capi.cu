@@ -1,0 +1,540 @@
+// f2_capi.cu -- the C ABI declared in include/f2cnn_b200.h: plans, batches, launch sequences.
+// Host-side only; every FLOP of the hot path runs in the kernels of f2_prep.cu, f2_fused.cu
+// and f2_post.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/f2cnn_b200.h"
+#include "f2_fused.cuh"
+#include "f2_post.cuh"
+#include "f2_prep.cuh"
+
+static_assert(F2_I16 == F2_DT_I16 && F2_F32 == F2_DT_F32 && F2_F64 == F2_DT_F64, "dtype codes");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define F2_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) return fail(F2_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+int round_up_tile(double v) { return (int)(ceil(v / f2::kTile) * f2::kTile); }
+
+// Per-stage float32 rounding whose SUM over the four stages is as close to 4*c as the
+// float32 lattice allows.  The four sections share their poles, so the first-order error of
+// the cascade response depends only on the sum of the per-stage denominator errors: choosing
+// m of 4 stages one ulp up cuts the effective coefficient error from ulp/2 to ulp/8.
+void dither4(double c, float out[4]) {
+    float r = (float)c;
+    float lo = ((double)r <= c) ? r : nextafterf(r, -INFINITY);
+    float hi = nextafterf(lo, INFINITY);
+    double frac = (c - (double)lo) / ((double)hi - (double)lo);
+    int m = (int)floor(4.0 * frac + 0.5);
+    for (int k = 0; k < 4; ++k) out[k] = (k < m) ? hi : lo;
+}
+
+void butter1(double cutoff_hz, double* b0, double* a1) {
+    // scipy.signal.butter(1, Wn, 'low'), Wn = cutoff/8000 (EnvelopeExtraction.py:47):
+    // pre-warp with fs=2, bilinear transform of 1/(s+1).
+    const double Wn = cutoff_hz / 8000.0;
+    const double w = 4.0 * tan(M_PI * Wn / 2.0);
+    *b0 = w / (4.0 + w);
+    *a1 = -(4.0 - w) / (4.0 + w);
+}
+
+}  // namespace
+
+struct f2_plan {
+    int device = 0;
+    int C = 0;
+    int c_pad = 0;
+    float* d_chan = nullptr;
+    int w_imag = 0, w_edge = 0, w_casc = 0;
+    double min_neg_log_r = 0.0;
+};
+
+struct f2_batch {
+    f2_plan* plan = nullptr;
+    int n_utts = 0;
+    int step = 1, phase = 0;
+    std::vector<f2::UttDesc> utts;
+    std::vector<long long> frame_off;
+    long long n_items = 0;
+    f2::UttDesc* d_utts = nullptr;
+    f2::Item* d_items = nullptr;
+    long long total_samples = 0, total_frames = 0, total_ring = 0;
+    int max_n = 0;
+    int min_log2 = 0, max_log2 = 0;
+};
+
+extern "C" {
+
+const char* f2_last_error(void) { return g_err; }
+int f2_abi_version(void) { return 1; }
+
+int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1) {
+    if (!b0 || !a1 || !(cutoff_hz > 0.0) || !(cutoff_hz < 8000.0))
+        return fail(F2_ERR_INVALID, "cutoff must be in (0, 8000) Hz, got %g", cutoff_hz);
+    butter1(cutoff_hz, b0, a1);
+    return F2_OK;
+}
+
+int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** out) {
+    if (!coefs || !out || n_channels <= 0) return fail(F2_ERR_INVALID, "f2_plan_create: bad arguments");
+    int ndev = 0;
+    F2_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(F2_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(F2_ERR_CUDA, "cannot select device %d", device);
+    cudaDeviceProp prop;
+    F2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(F2_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    const int C = n_channels;
+    const int c_pad = (int)align_up((size_t)C, 32);
+    std::vector<float> par((size_t)f2::kNumChanPar * c_pad, 0.f);
+    double min_nlr = 1e300;
+    for (int c = 0; c < C; ++c) {
+        const double* k = coefs + (size_t)c * 10;
+        const double A0 = k[0], A2 = k[5], B0 = k[6], B1 = k[7], B2 = k[8], gain = k[9];
+        if (A2 != 0.0) return fail(F2_ERR_UNSUPPORTED, "channel %d: A2 != 0 is not a make_erb_filters bank", c);
+        if (!(B0 != 0.0) || !(gain > 0.0) || !isfinite(gain))
+            return fail(F2_ERR_INVALID, "channel %d: B0 == 0 or gain <= 0", c);
+        const double b1 = B1 / B0, b2 = B2 / B0;
+        if (!(b2 > 0.0 && b2 < 1.0) || !(fabs(b1) < 1.0 + b2))
+            return fail(F2_ERR_UNSUPPORTED, "channel %d: poles are not a stable complex pair", c);
+        const double gq = pow(gain, 0.25);
+        par[(size_t)f2::P_A0 * c_pad + c] = (float)(A0 / B0 / gq);
+        for (int s = 0; s < 4; ++s) par[(size_t)(f2::P_A1 + s) * c_pad + c] = (float)(k[1 + s] / B0 / gq);
+        float cq[4], ncy[4];
+        dither4(b2, cq);
+        dither4(-(1.0 + b1 + b2), ncy);
+        for (int s = 0; s < 4; ++s) {
+            par[(size_t)(f2::P_CQ + s) * c_pad + c] = cq[s];
+            par[(size_t)(f2::P_NCY + s) * c_pad + c] = ncy[s];
+        }
+        min_nlr = std::min(min_nlr, -0.5 * log(b2));  // -ln(pole radius)
+    }
+    f2_plan* p = new (std::nothrow) f2_plan();
+    if (!p) return fail(F2_ERR_INVALID, "out of host memory");
+    p->device = device;
+    p->C = C;
+    p->c_pad = c_pad;
+    p->min_neg_log_r = min_nlr;
+    // truncated-history lengths: r^W * W^3 envelope of the 4-section cascade below float32
+    // resolution (measured against the float64 oracle: 21.5/-ln r -> 1e-9, 29/-ln r -> 1e-12)
+    p->w_imag = round_up_tile(21.5 / min_nlr);
+    p->w_edge = round_up_tile(29.0 / min_nlr);
+    p->w_casc = p->w_edge;
+    cudaError_t e = cudaMalloc(&p->d_chan, par.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_chan, par.data(), par.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = f2::init_twiddles(0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (p->d_chan) cudaFree(p->d_chan);
+        delete p;
+        return fail(F2_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return F2_OK;
+}
+
+int f2_plan_destroy(f2_plan* plan) {
+    if (!plan) return F2_OK;
+    DeviceGuard guard(plan->device);
+    if (plan->d_chan) cudaFree(plan->d_chan);
+    delete plan;
+    return F2_OK;
+}
+
+int f2_plan_channels(const f2_plan* plan) { return plan ? plan->C : 0; }
+
+int f2_plan_set_warmup(f2_plan* plan, int w_imag, int w_edge, int w_casc) {
+    if (!plan) return fail(F2_ERR_INVALID, "null plan");
+    if (w_imag > 0) plan->w_imag = round_up_tile(w_imag);
+    if (w_edge > 0) plan->w_edge = round_up_tile(w_edge);
+    if (w_casc > 0) plan->w_casc = round_up_tile(w_casc);
+    return F2_OK;
+}
+
+int f2_plan_get_warmup(const f2_plan* plan, int* w_imag, int* w_edge, int* w_casc) {
+    if (!plan) return fail(F2_ERR_INVALID, "null plan");
+    if (w_imag) *w_imag = plan->w_imag;
+    if (w_edge) *w_edge = plan->w_edge;
+    if (w_casc) *w_casc = plan->w_casc;
+    return F2_OK;
+}
+
+int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step, int phase, int64_t target_items,
+                    f2_batch** out) {
+    if (!plan || !out || n_utts < 0 || (n_utts > 0 && !lengths) || step <= 0 || phase < 0)
+        return fail(F2_ERR_INVALID, "f2_batch_create: bad arguments");
+    f2_batch* b = new (std::nothrow) f2_batch();
+    if (!b) return fail(F2_ERR_INVALID, "out of host memory");
+    b->plan = plan;
+    b->n_utts = n_utts;
+    b->step = step;
+    b->phase = phase;
+    b->utts.resize((size_t)n_utts);
+    b->frame_off.assign((size_t)n_utts + 1, 0);
+    b->min_log2 = 64;
+    b->max_log2 = 0;
+    long long wave = 0, ring = 0, frames = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        const int64_t n = lengths[u];
+        if (n < 0 || n > ((int64_t)1 << 25)) {
+            delete b;
+            return fail(F2_ERR_UNSUPPORTED, "utterance %d: %lld samples (supported: 0 .. 2^25)", u, (long long)n);
+        }
+        int lg = 0;
+        while (((int64_t)1 << lg) < n) ++lg;  // N2 = 2^ceil(log2 n)   (EnvelopeExtraction.py:29)
+        f2::UttDesc& d = b->utts[(size_t)u];
+        d.wave_off = wave;
+        d.ring_off = ring;
+        d.full_off = wave;
+        d.dec_off = frames;
+        d.n = (int)n;
+        d.N2 = 1 << lg;
+        d.log2N2 = lg;
+        d.n_dec = n > phase ? (int)((n - phase + step - 1) / step) : 0;
+        b->frame_off[(size_t)u] = frames;
+        wave += n;
+        ring += (long long)align_up((size_t)d.N2, f2::kRingAlign);
+        frames += d.n_dec;
+        if (n > 0) {
+            b->min_log2 = std::min(b->min_log2, lg);
+            b->max_log2 = std::max(b->max_log2, lg);
+            b->max_n = std::max(b->max_n, (int)n);
+        }
+    }
+    if (b->min_log2 > b->max_log2) b->min_log2 = b->max_log2 = 0;
+    b->frame_off[(size_t)n_utts] = frames;
+    b->total_samples = wave;
+    b->total_frames = frames;
+    b->total_ring = ring;
+
+    // ---- work items: (utterance, channel block, time chunk) -------------------------------
+    const int cblocks = (plan->C + f2::kChanPerBlock - 1) / f2::kChanPerBlock;
+    if (target_items <= 0) target_items = 148 * 4 * 4;  // 4 resident CTAs per SM, 4 waves
+    long long whole = 0;
+    for (int u = 0; u < n_utts; ++u) whole += lengths[u] > 0 ? cblocks : 0;
+    long long seg = (long long)1 << 40;  // no splitting
+    if (whole < target_items && wave > 0) {
+        // split so that about target_items chunks exist, but never below 2048 samples
+        // (each chunk pays w_casc (+ w_lpf) samples of warm-up)
+        seg = (long long)align_up((size_t)std::max<long long>(wave * cblocks / target_items, 2048), f2::kTile);
+    }
+    std::vector<f2::Item> items;
+    for (int u = 0; u < n_utts; ++u) {
+        const int n = b->utts[(size_t)u].n;
+        if (n <= 0) continue;
+        const long long nseg = std::max<long long>(1, (n + seg - 1) / seg);
+        const long long len = (long long)align_up((size_t)((n + nseg - 1) / nseg), f2::kTile);
+        for (long long t0 = 0; t0 < n; t0 += len)
+            for (int cb = 0; cb < cblocks; ++cb) {
+                f2::Item it;
+                it.utt = u;
+                it.cblock = cb;
+                it.t0 = (int)t0;
+                it.t1 = (int)std::min<long long>(n, t0 + len);
+                items.push_back(it);
+            }
+    }
+    // longest first: the hardware dispatches CTAs in index order, so the tail is short items
+    std::stable_sort(items.begin(), items.end(), [](const f2::Item& a, const f2::Item& c) {
+        return (a.t1 - a.t0) > (c.t1 - c.t0);
+    });
+    b->n_items = (long long)items.size();
+
+    DeviceGuard guard(plan->device);
+    cudaError_t e = cudaSuccess;
+    if (n_utts > 0) {
+        e = cudaMalloc(&b->d_utts, sizeof(f2::UttDesc) * (size_t)n_utts);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(b->d_utts, b->utts.data(), sizeof(f2::UttDesc) * (size_t)n_utts, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && !items.empty()) {
+        e = cudaMalloc(&b->d_items, sizeof(f2::Item) * items.size());
+        if (e == cudaSuccess)
+            e = cudaMemcpy(b->d_items, items.data(), sizeof(f2::Item) * items.size(), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        if (b->d_utts) cudaFree(b->d_utts);
+        if (b->d_items) cudaFree(b->d_items);
+        delete b;
+        return fail(F2_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return F2_OK;
+}
+
+int f2_batch_destroy(f2_batch* batch) {
+    if (!batch) return F2_OK;
+    DeviceGuard guard(batch->plan->device);
+    if (batch->d_utts) cudaFree(batch->d_utts);
+    if (batch->d_items) cudaFree(batch->d_items);
+    delete batch;
+    return F2_OK;
+}
+
+int64_t f2_batch_total_samples(const f2_batch* b) { return b ? b->total_samples : 0; }
+int64_t f2_batch_total_frames(const f2_batch* b) { return b ? b->total_frames : 0; }
+int64_t f2_batch_num_items(const f2_batch* b) { return b ? b->n_items : 0; }
+
+int f2_batch_frame_offsets(const f2_batch* b, int64_t* frame_offsets) {
+    if (!b || !frame_offsets) return fail(F2_ERR_INVALID, "f2_batch_frame_offsets: bad arguments");
+    for (size_t i = 0; i < b->frame_off.size(); ++i) frame_offsets[i] = b->frame_off[i];
+    return F2_OK;
+}
+
+// workspace: [Z floats][xz float2][G floats][gfb_t][env_t], each section 256-byte aligned
+static size_t ws_ring_bytes(long long total_ring) { return align_up((size_t)total_ring * 4, 256); }
+static size_t ws_full_bytes(const f2_batch* b) {
+    return align_up((size_t)b->total_samples * (size_t)b->plan->C * sizeof(float), 256);
+}
+
+size_t f2_batch_workspace_bytes(const f2_batch* b, int want_full_gfb, int want_full_env) {
+    if (!b) return 0;
+    size_t s = 4 * ws_ring_bytes(b->total_ring);
+    if (want_full_gfb) s += ws_full_bytes(b);
+    if (want_full_env) s += ws_full_bytes(b);
+    return s + 256;
+}
+
+int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!b || !a) return fail(F2_ERR_INVALID, "f2_batch_run: null batch/args");
+    if (b->total_samples == 0) return F2_OK;
+    if (!a->wave || a->wave_dtype < F2_I16 || a->wave_dtype > F2_F64)
+        return fail(F2_ERR_INVALID, "f2_batch_run: wave pointer/dtype");
+    if ((a->gfb && a->gfb_dtype != F2_F32 && a->gfb_dtype != F2_F64) ||
+        (a->env && a->env_dtype != F2_F32 && a->env_dtype != F2_F64))
+        return fail(F2_ERR_INVALID, "f2_batch_run: output dtype must be F2_F32 or F2_F64");
+    const bool want_gfb = a->gfb != nullptr;
+    const bool want_env_scratch = a->env != nullptr && a->env_t == nullptr;
+    const size_t need = f2_batch_workspace_bytes(b, want_gfb, want_env_scratch);
+    if (!workspace || workspace_bytes < need)
+        return fail(F2_ERR_WORKSPACE, "workspace %zu bytes, need %zu", workspace_bytes, need);
+    double b0 = 0.0, a1 = 0.0;
+    if (a->lpf) {
+        if (!(a->cutoff_hz > 0.0) || !(a->cutoff_hz < 8000.0))
+            return fail(F2_ERR_INVALID, "cutoff must be in (0, 8000) Hz, got %g", a->cutoff_hz);
+        butter1(a->cutoff_hz, &b0, &a1);
+    }
+    f2_plan* plan = b->plan;
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(F2_ERR_CUDA, "cannot select device %d", plan->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    char* ws = (char*)align_up((size_t)workspace, 256);
+    const size_t rb = ws_ring_bytes(b->total_ring);
+    float* Z = (float*)ws;
+    float2* xz = (float2*)(ws + rb);
+    float* G = (float*)(ws + 3 * rb);
+    char* cur = ws + 4 * rb;
+    float* gfb_t = nullptr;
+    float* env_t = a->env_t;
+    if (want_gfb) {
+        gfb_t = (float*)cur;
+        cur += ws_full_bytes(b);
+    }
+    if (want_env_scratch) {
+        env_t = (float*)cur;
+        cur += ws_full_bytes(b);
+    }
+    const bool need_env = env_t != nullptr || a->dec != nullptr;
+
+    f2::PrepParams pp;
+    pp.utts = b->d_utts;
+    pp.wave = a->wave;
+    pp.wave_dtype = a->wave_dtype;
+    pp.Z = Z;
+    pp.xz = xz;
+    pp.G = G;
+    pp.hilbert = need_env ? 1 : 0;
+    f2::HostPrepInfo hp;
+    hp.n_utts = b->n_utts;
+    hp.min_log2N2 = b->min_log2;
+    hp.max_log2N2 = b->max_log2;
+    F2_CUDA(f2::launch_prep(pp, hp, stream));
+
+    f2::FusedParams fp;
+    fp.utts = b->d_utts;
+    fp.items = b->d_items;
+    fp.chan = plan->d_chan;
+    fp.xz = xz;
+    fp.G = G;
+    fp.gfb_t = gfb_t;
+    fp.env_t = env_t;
+    fp.dec = a->dec;
+    fp.C = plan->C;
+    fp.c_pad = plan->c_pad;
+    fp.step = b->step;
+    fp.phase = b->phase;
+    fp.lpf = a->lpf ? 1 : 0;
+    fp.lp_k = (float)(-a1);
+    fp.lp_b0 = (float)b0;
+    fp.w_imag = plan->w_imag;
+    fp.w_edge = plan->w_edge;
+    fp.w_casc = plan->w_casc;
+    // low-pass warm-up of a mid-signal chunk: |a1|^W < 1e-7
+    fp.w_lpf = a->lpf ? round_up_tile(log(1e-7) / log(-a1)) : 0;
+    F2_CUDA(f2::launch_fused(fp, (int)b->n_items, stream));
+
+    if (a->gfb)
+        F2_CUDA(f2::launch_transpose_convert(b->d_utts, b->n_utts, b->max_n, gfb_t, a->gfb, a->gfb_dtype, plan->C,
+                                             stream));
+    if (a->env)
+        F2_CUDA(f2::launch_transpose_convert(b->d_utts, b->n_utts, b->max_n, env_t, a->env, a->env_dtype, plan->C,
+                                             stream));
+    return F2_OK;
+}
+
+// ---- stand-alone envelope rows ------------------------------------------------------------
+namespace {
+struct RowLayout {
+    int lg;
+    long long ring_len;
+    long long rows_pad;
+};
+RowLayout row_layout(int64_t rows, int64_t n) {
+    RowLayout r;
+    r.lg = 0;
+    while (((int64_t)1 << r.lg) < n) ++r.lg;
+    r.ring_len = (long long)align_up((size_t)1 << r.lg, f2::kRingAlign);
+    r.rows_pad = (long long)align_up((size_t)rows, 4);
+    return r;
+}
+__global__ void rows_desc_kernel(f2::UttDesc* d, long long rows, long long rows_pad, int n, int lg,
+                                 long long ring_len) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows_pad) return;
+    f2::UttDesc u;
+    u.wave_off = r * n;
+    u.ring_off = (r < rows ? r : 0) * ring_len;
+    u.full_off = r * n;
+    u.dec_off = 0;
+    u.n = r < rows ? n : 0;
+    u.N2 = 1 << lg;
+    u.n_dec = 0;
+    u.log2N2 = lg;
+    d[r] = u;
+}
+}  // namespace
+
+size_t f2_envelope_rows_workspace_bytes(int64_t rows, int64_t n) {
+    if (rows <= 0 || n <= 0) return 256;
+    const RowLayout r = row_layout(rows, n);
+    return align_up((size_t)r.rows_pad * sizeof(f2::UttDesc), 256) + 3 * ws_ring_bytes(r.ring_len * rows) + 256;
+}
+
+int f2_envelope_rows(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64_t n, int lpf,
+                     double cutoff_hz, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+                     void* stream_) {
+    if (!plan || rows < 0 || n < 0) return fail(F2_ERR_INVALID, "f2_envelope_rows: bad arguments");
+    if (rows == 0 || n == 0) return F2_OK;
+    if (!matrix || !out || dtype < F2_I16 || dtype > F2_F64 || (out_dtype != F2_F32 && out_dtype != F2_F64))
+        return fail(F2_ERR_INVALID, "f2_envelope_rows: pointer/dtype");
+    if (n > ((int64_t)1 << 25)) return fail(F2_ERR_UNSUPPORTED, "row length %lld > 2^25", (long long)n);
+    if (rows > (1 << 24)) return fail(F2_ERR_UNSUPPORTED, "too many rows");
+    const size_t need = f2_envelope_rows_workspace_bytes(rows, n);
+    if (!workspace || workspace_bytes < need)
+        return fail(F2_ERR_WORKSPACE, "workspace %zu bytes, need %zu", workspace_bytes, need);
+    double b0 = 0.0, a1 = 0.0;
+    if (lpf) {
+        if (!(cutoff_hz > 0.0) || !(cutoff_hz < 8000.0))
+            return fail(F2_ERR_INVALID, "cutoff must be in (0, 8000) Hz, got %g", cutoff_hz);
+        butter1(cutoff_hz, &b0, &a1);
+    }
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(F2_ERR_CUDA, "cannot select device %d", plan->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const RowLayout r = row_layout(rows, n);
+    char* ws = (char*)align_up((size_t)workspace, 256);
+    f2::UttDesc* d_rows = (f2::UttDesc*)ws;
+    ws += align_up((size_t)r.rows_pad * sizeof(f2::UttDesc), 256);
+    const size_t rb = ws_ring_bytes(r.ring_len * rows);
+    float* Z = (float*)ws;
+    float2* xz = (float2*)(ws + rb);
+    rows_desc_kernel<<<(unsigned)((r.rows_pad + 127) / 128), 128, 0, stream>>>(d_rows, rows, r.rows_pad, (int)n, r.lg,
+                                                                              r.ring_len);
+    F2_CUDA(cudaGetLastError());
+    f2::PrepParams pp;
+    pp.utts = d_rows;
+    pp.wave = matrix;
+    pp.wave_dtype = dtype;
+    pp.Z = Z;
+    pp.xz = xz;
+    pp.G = nullptr;
+    pp.hilbert = 1;
+    f2::HostPrepInfo hp;
+    hp.n_utts = (int)rows;
+    hp.min_log2N2 = hp.max_log2N2 = r.lg;
+    F2_CUDA(f2::launch_prep(pp, hp, stream));
+    F2_CUDA(f2::launch_rows_envelope(d_rows, (int)r.rows_pad, xz, lpf ? 1 : 0, (float)(-a1), (float)b0, out, out_dtype,
+                                     stream));
+    return F2_OK;
+}
+
+// ---- windowing ----------------------------------------------------------------------------
+int f2_gather_windows(const float* frames, int n_channels, const int64_t* base_rows, int64_t n_windows, int dots,
+                      int64_t stride_rows, float* out, void* stream) {
+    if (n_windows == 0) return F2_OK;
+    if (!frames || !base_rows || !out || n_channels <= 0 || dots <= 0 || n_windows < 0)
+        return fail(F2_ERR_INVALID, "f2_gather_windows: bad arguments");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    F2_CUDA(f2::launch_gather_rows(frames, (const long long*)base_rows, n_windows, dots, stride_rows, n_channels, out,
+                                   (cudaStream_t)stream));
+    return F2_OK;
+}
+
+int f2_gather_index(const float* src, int n_channels, const int64_t* idx, int64_t n_idx, float* out, void* stream) {
+    if (n_idx == 0) return F2_OK;
+    if (!src || !idx || !out || n_channels <= 0 || n_idx < 0) return fail(F2_ERR_INVALID, "f2_gather_index: bad arguments");
+    F2_CUDA(f2::launch_gather_index(src, (const long long*)idx, n_idx, n_channels, out, (cudaStream_t)stream));
+    return F2_OK;
+}
+
+int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int64_t i0, int64_t i1, int normalize,
+                    void* out, int out_dtype, int* bad_flag, void* stream) {
+    if (i1 <= i0) return F2_OK;
+    if (!env_t || !out || n_channels <= 0 || dots <= 0 || step <= 0 || i0 < 0 || (normalize && !bad_flag))
+        return fail(F2_ERR_INVALID, "f2_dense_frames: bad arguments");
+    F2_CUDA(f2::launch_dense_frames(env_t, n_channels, dots, step, i0, i1, normalize, out, out_dtype, bad_flag,
+                                    (cudaStream_t)stream));
+    return F2_OK;
+}
+
+}  // extern "C"

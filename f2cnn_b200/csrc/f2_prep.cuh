@@ -1,0 +1,31 @@
+// f2_prep.cuh -- launch interface of the ring / Hilbert pre-pass (f2_prep.cu).
+#pragma once
+#include "f2_common.cuh"
+
+// sample dtypes accepted at the C-ABI (mirrors include/f2cnn_b200.h)
+#define F2_DT_I16 0
+#define F2_DT_F32 1
+#define F2_DT_F64 2
+
+namespace f2 {
+
+struct PrepParams {
+    const UttDesc* utts;
+    const void* wave;  // flat samples, dtype wave_dtype
+    int wave_dtype;
+    float* Z;          // FFT scratch / xi: ring_len floats per utterance
+    float2* xz;        // out: (x, xi) rings
+    float* G;          // out: injection kernel rings (nullable: not needed for plain Hilbert)
+    int hilbert;       // 0: filterbank-only run, skip the FFTs and leave xi = 0
+};
+
+struct HostPrepInfo {
+    int n_utts;
+    int min_log2N2;
+    int max_log2N2;
+};
+
+cudaError_t init_twiddles(cudaStream_t stream);
+cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t stream);
+
+}  // namespace f2

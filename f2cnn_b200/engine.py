@@ -1,0 +1,230 @@
+"""Host-side engine: plans, batches and launch helpers over the C ABI.
+
+PyTorch is used only as plumbing (device memory, pinned host buffers, streams); every
+computation of the hot path happens in libf2cnn_b200.so.  Nothing here falls back to
+numpy/scipy/torch math: without the library or a CUDA device the calls raise."""
+import ctypes
+import hashlib
+import threading
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import F2_F32, F2_F64, F2_I16, RunArgs, check
+
+_NP2F2 = {np.dtype(np.int16): F2_I16, np.dtype(np.float32): F2_F32, np.dtype(np.float64): F2_F64}
+_T2F2 = {torch.int16: F2_I16, torch.float32: F2_F32, torch.float64: F2_F64}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("f2cnn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr(stream):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def lowpass_coefficients(cutoff_hz):
+    """(b0, a1) of butter(1, cutoff/8000, 'low') -- reference EnvelopeExtraction.py:47."""
+    b0 = ctypes.c_double()
+    a1 = ctypes.c_double()
+    check(_native.lib().f2_lowpass_coefficients(float(cutoff_hz), ctypes.byref(b0), ctypes.byref(a1)))
+    return b0.value, a1.value
+
+
+class Plan:
+    """One gammatone filterbank on one device.  coefs = make_erb_filters output (C,10)."""
+
+    def __init__(self, coefs, device=None):
+        _require_cuda()
+        coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+        if coefs.ndim != 2 or coefs.shape[1] != 10:
+            raise ValueError("coefs must be (n_channels, 10) as returned by make_erb_filters")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.n_channels = int(coefs.shape[0])
+        self.coefs = coefs
+        self._h = ctypes.c_void_p()
+        check(_native.lib().f2_plan_create(coefs.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), self.n_channels,
+                                           self.device.index, ctypes.byref(self._h)))
+        self._ws = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _native.lib().f2_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
+
+    def set_warmup(self, w_imag=0, w_edge=0, w_casc=0):
+        check(_native.lib().f2_plan_set_warmup(self._h, int(w_imag), int(w_edge), int(w_casc)))
+
+    def get_warmup(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(_native.lib().f2_plan_get_warmup(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def batch(self, lengths, step=160, phase=0, target_items=0):
+        return Batch(self, lengths, step, phase, target_items)
+
+    def workspace(self, nbytes):
+        """Grow-only scratch shared by this plan's launches (caller-owned per the C ABI)."""
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # -- stand-alone envelope of matrix rows (ExtractEnvelopeFromMatrix on foreign data) ----
+    def envelope_rows(self, matrix_dev, lpf, cutoff, out_dtype=torch.float64, stream=None):
+        rows, n = matrix_dev.shape
+        out = torch.empty((rows, n), dtype=out_dtype, device=self.device)
+        if rows == 0 or n == 0:
+            return out
+        L = _native.lib()
+        ws = self.workspace(L.f2_envelope_rows_workspace_bytes(rows, n))
+        check(L.f2_envelope_rows(self._h, _ptr(matrix_dev), _T2F2[matrix_dev.dtype], rows, n, int(bool(lpf)),
+                                 float(cutoff), _ptr(out), _T2F2[out_dtype], _ptr(ws), ws.numel(),
+                                 _stream_ptr(stream)))
+        return out
+
+
+class Batch:
+    """A set of utterances (by length) prepared for repeated runs on one plan."""
+
+    def __init__(self, plan, lengths, step=160, phase=0, target_items=0):
+        self.plan = plan
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(-1)
+        self.n_utts = int(self.lengths.shape[0])
+        self.step, self.phase = int(step), int(phase)
+        self._h = ctypes.c_void_p()
+        L = _native.lib()
+        check(L.f2_batch_create(plan._h, self.lengths.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), self.n_utts,
+                                self.step, self.phase, int(target_items), ctypes.byref(self._h)))
+        self.total_samples = int(L.f2_batch_total_samples(self._h))
+        self.total_frames = int(L.f2_batch_total_frames(self._h))
+        self.num_items = int(L.f2_batch_num_items(self._h))
+        self.frame_offsets = np.zeros(self.n_utts + 1, dtype=np.int64)
+        check(L.f2_batch_frame_offsets(self._h, self.frame_offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+        self.sample_offsets = np.zeros(self.n_utts + 1, dtype=np.int64)
+        np.cumsum(self.lengths, out=self.sample_offsets[1:])
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _native.lib().f2_batch_destroy(h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
+
+    def workspace_bytes(self, want_full_gfb=False, want_full_env=False):
+        return int(_native.lib().f2_batch_workspace_bytes(self._h, int(want_full_gfb), int(want_full_env)))
+
+    def run(self, wave_dev, lpf=False, cutoff=100, gfb=None, env=None, env_t=False, dec=False, stream=None,
+            out=None):
+        """wave_dev: flat device tensor (int16/float32/float64) of total_samples.
+        gfb/env: None or torch.float64/float32 -> (C*total_samples,) reference-layout blocks;
+        env_t: time-major [total_samples, C] float32; dec: [total_frames, C] float32.
+        `out` may carry preallocated tensors under the same keys."""
+        plan = self.plan
+        C = plan.n_channels
+        if wave_dev.numel() != self.total_samples:
+            raise ValueError("wave has %d samples, batch expects %d" % (wave_dev.numel(), self.total_samples))
+        if wave_dev.device != plan.device:
+            raise ValueError("wave is on %s, plan on %s" % (wave_dev.device, plan.device))
+        res = {} if out is None else dict(out)
+        if gfb is not None and "gfb" not in res:
+            res["gfb"] = torch.empty(C * self.total_samples, dtype=gfb, device=plan.device)
+        if env is not None and "env" not in res:
+            res["env"] = torch.empty(C * self.total_samples, dtype=env, device=plan.device)
+        if env_t and "env_t" not in res:
+            res["env_t"] = torch.empty((self.total_samples, C), dtype=torch.float32, device=plan.device)
+        if dec and "dec" not in res:
+            res["dec"] = torch.empty((self.total_frames, C), dtype=torch.float32, device=plan.device)
+        a = RunArgs()
+        a.wave = wave_dev.data_ptr()
+        a.wave_dtype = _T2F2[wave_dev.dtype]
+        a.lpf = int(bool(lpf))
+        a.cutoff_hz = float(cutoff) if lpf else 0.0
+        g, e = res.get("gfb"), res.get("env")
+        a.gfb = g.data_ptr() if g is not None else None
+        a.gfb_dtype = _T2F2[g.dtype] if g is not None else F2_F64
+        a.env = e.data_ptr() if e is not None else None
+        a.env_dtype = _T2F2[e.dtype] if e is not None else F2_F64
+        a.env_t = res["env_t"].data_ptr() if "env_t" in res else None
+        a.dec = res["dec"].data_ptr() if "dec" in res else None
+        need = self.workspace_bytes(g is not None, e is not None and "env_t" not in res)
+        ws = plan.workspace(need)
+        check(_native.lib().f2_batch_run(self._h, ctypes.byref(a), _ptr(ws), ws.numel(), _stream_ptr(stream)))
+        return res
+
+
+# ---- windowing helpers ---------------------------------------------------------------------
+def gather_windows(frames_dev, base_rows_dev, dots, stride_rows=1, out=None, stream=None):
+    """out[w, j, :] = frames[base_rows[w] + j*stride_rows, :]  (InputGenerator.py:73-80)."""
+    n, C = int(base_rows_dev.numel()), int(frames_dev.shape[1])
+    if out is None:
+        out = torch.empty((n, dots, C), dtype=torch.float32, device=frames_dev.device)
+    check(_native.lib().f2_gather_windows(_ptr(frames_dev), C, _ptr(base_rows_dev), n, int(dots), int(stride_rows),
+                                          _ptr(out), _stream_ptr(stream)))
+    return out
+
+
+def gather_index(src_dev, idx_dev, out=None, stream=None):
+    n, C = int(idx_dev.numel()), int(src_dev.shape[1])
+    if out is None:
+        out = torch.empty((n, C), dtype=torch.float32, device=src_dev.device)
+    check(_native.lib().f2_gather_index(_ptr(src_dev), C, _ptr(idx_dev), n, _ptr(out), _stream_ptr(stream)))
+    return out
+
+
+def dense_frames(env_t_dev, dots, step, i0, i1, normalize=False, out_dtype=torch.float64, stream=None):
+    """Frames i0..i1 of Evaluating.py:70-78 (+ Training.normalizeInput when normalize)."""
+    C = int(env_t_dev.shape[1])
+    out = torch.empty((max(i1 - i0, 0), dots, C), dtype=out_dtype, device=env_t_dev.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=env_t_dev.device)
+    check(_native.lib().f2_dense_frames(_ptr(env_t_dev), C, int(dots), int(step), int(i0), int(i1),
+                                        int(bool(normalize)), _ptr(out), _T2F2[out_dtype], _ptr(flag),
+                                        _stream_ptr(stream)))
+    return out, flag
+
+
+# ---- plan cache for the numpy-in / numpy-out drop-in functions -----------------------------
+_plans = {}
+_plans_lock = threading.Lock()
+
+
+def plan_for(coefs, device=None):
+    """Plans are immutable; cache them by the bytes of the coefficient matrix."""
+    _require_cuda()
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    dev = torch.cuda.current_device() if device is None else int(device)
+    key = (hashlib.sha1(coefs.tobytes()).hexdigest(), coefs.shape, dev)
+    with _plans_lock:
+        p = _plans.get(key)
+        if p is None:
+            p = Plan(coefs, dev)
+            _plans[key] = p
+        return p
+
+
+_generic_plan = {}
+
+
+def any_plan(device=None):
+    """A plan is only a device handle for the filterbank-independent entry points."""
+    dev = torch.cuda.current_device() if device is None else int(device)
+    with _plans_lock:
+        for (k, shape, d), p in _plans.items():
+            if d == dev:
+                return p
+    from .gammatone import filters
+    return plan_for(filters.make_erb_filters(16000, filters.centre_freqs(16000, 4, 100)), dev)

@@ -1,0 +1,131 @@
+/*
+ * f2cnn_b200.h -- C ABI of libf2cnn_b200.so: the B200 (sm_100a) implementation of F2CNN's
+ * feature-extraction hot path (gammatone filterbank -> ENV1 envelope -> windowing).
+ *
+ * The reference (tictacmenthe/F2CNN) is pure Python and has no FFI of its own; its boundary
+ * is a set of module-level numpy functions.  Each entry point below
+ * names the reference function (file:line under the reference tree) whose arithmetic it
+ * replaces; f2cnn_b200/ mirrors those Python signatures on top of this ABI, and
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (F2_OK == 0) and never throws; f2_last_error() gives the message of the calling thread's
+ * last failure.  All data pointers are DEVICE pointers on the plan's device unless the
+ * parameter is documented as host; `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream).  The caller owns every buffer, including the workspace.  A plan is
+ * immutable after creation and may be shared by several streams; a batch may be run on one
+ * stream at a time.  There is no CPU fallback: without a CUDA device every call fails with
+ * F2_ERR_CUDA.
+ */
+#ifndef F2CNN_B200_H
+#define F2CNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define F2_API __attribute__((visibility("default")))
+#else
+#define F2_API
+#endif
+
+#define F2_OK 0
+#define F2_ERR_INVALID 1     /* bad argument */
+#define F2_ERR_CUDA 2        /* CUDA runtime error (see f2_last_error) */
+#define F2_ERR_WORKSPACE 3   /* workspace too small */
+#define F2_ERR_UNSUPPORTED 4 /* size outside the supported range */
+
+/* sample / matrix element types */
+#define F2_I16 0
+#define F2_F32 1
+#define F2_F64 2
+
+typedef struct f2_plan f2_plan;
+typedef struct f2_batch f2_batch;
+
+F2_API const char* f2_last_error(void);
+/* ABI version of the library (bumped on any signature change). */
+F2_API int f2_abi_version(void);
+
+/* ---- plan: one gammatone filterbank ----------------------------------------------------
+ * coefs: HOST pointer to the (n_channels, 10) float64 matrix returned by
+ * gammatone.filters.make_erb_filters (gammatone/filters.py:186-190: columns
+ * A0, A11, A12, A13, A14, A2, B0, B1, B2, gain).  Derives the float32 per-channel
+ * parameter block in float64 and uploads it to `device`. */
+F2_API int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** out);
+F2_API int f2_plan_destroy(f2_plan* plan);
+F2_API int f2_plan_channels(const f2_plan* plan);
+/* Warm-up lengths in samples (rounded up to multiples of 256); <= 0 keeps the default that
+ * plan creation derived from the slowest pole.  w_imag: periodic start of the Hilbert path;
+ * w_edge: tail used for the edge residuals; w_casc: warm-up of a chunk that starts mid-signal. */
+F2_API int f2_plan_set_warmup(f2_plan* plan, int w_imag, int w_edge, int w_casc);
+F2_API int f2_plan_get_warmup(const f2_plan* plan, int* w_imag, int* w_edge, int* w_casc);
+
+/* ---- batch: a set of utterances laid out for one launch sequence ------------------------
+ * lengths: HOST array of n_utts sample counts; utterance u occupies samples
+ * [sum(lengths[:u]), +lengths[u]) of the flat wave buffer.  step/phase define the decimated
+ * grid t = phase + j*step (InputGenerator.py:65 STEP = int(FRAMERATE*SAMPLING_PERIOD/1e6);
+ * LabelDataGenerator.py:48-50 puts every timepoint on that grid).  target_items <= 0 lets
+ * the library choose how finely long utterances are split into time chunks. */
+F2_API int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step, int phase, int64_t target_items,
+                    f2_batch** out);
+F2_API int f2_batch_destroy(f2_batch* batch);
+F2_API int64_t f2_batch_total_samples(const f2_batch* batch);
+F2_API int64_t f2_batch_total_frames(const f2_batch* batch);
+F2_API int64_t f2_batch_num_items(const f2_batch* batch);
+/* frame_offsets: HOST array of n_utts+1: first decimated frame of each utterance. */
+F2_API int f2_batch_frame_offsets(const f2_batch* batch, int64_t* frame_offsets);
+F2_API size_t f2_batch_workspace_bytes(const f2_batch* batch, int want_full_gfb, int want_full_env);
+
+typedef struct f2_run_args {
+    const void* wave; /* flat samples of all utterances, wave_dtype                        */
+    int wave_dtype;   /* F2_I16 (WAV), F2_F32, F2_F64 (noise-mixed, Evaluating.py:200)     */
+    int lpf;          /* LPF flag of ExtractEnvelopeFromMatrix (EnvelopeExtraction.py:51)  */
+    double cutoff_hz; /* CUTOFF; Nyquist fixed at 8000 Hz as in EnvelopeExtraction.py:47   */
+    void* gfb;        /* out, nullable: erb_filterbank result, (C,n_u) blocks back to back */
+    int gfb_dtype;    /* F2_F64 (reference dtype) or F2_F32                                */
+    void* env;        /* out, nullable: ExtractEnvelopeFromMatrix result, same layout      */
+    int env_dtype;
+    float* env_t;     /* out, nullable: envelope time-major [sum n][C] float32             */
+    float* dec;       /* out, nullable: decimated envelope frames [total_frames][C] float32 */
+} f2_run_args;
+
+/* Replaces, fused: filters.erb_filterbank (gammatone/filters.py:195-239),
+ * ExtractEnvelopeFromMatrix (EnvelopeExtraction.py:51-67) and the decimated reads of
+ * GenerateInputData (InputGenerator.py:73-80). */
+F2_API int f2_batch_run(f2_batch* batch, const f2_run_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stand-alone envelope of arbitrary matrix rows ---------------------------------------
+ * ExtractEnvelopeFromMatrix(matrix, LPF, CUTOFF) for a matrix that did not come from this
+ * library (e.g. loaded from .GFB.npy, EnvelopeExtraction.py:70-83): rows x n, row-major. */
+F2_API size_t f2_envelope_rows_workspace_bytes(int64_t rows, int64_t n);
+F2_API int f2_envelope_rows(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64_t n, int lpf,
+                     double cutoff_hz, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---- windowing ---------------------------------------------------------------------------
+ * out[w][j][c] = frames[base_rows[w] + j*stride_rows][c], j < dots: the window gather of
+ * InputGenerator.py:73-80 on decimated frames (base = frame of center - RADIUS*STEP,
+ * stride 1) or on a time-major full-rate envelope (base = center - RADIUS*STEP, stride STEP). */
+F2_API int f2_gather_windows(const float* frames, int n_channels, const int64_t* base_rows, int64_t n_windows, int dots,
+                      int64_t stride_rows, float* out, void* stream);
+/* out[i][c] = src[idx[i]][c]: arbitrary rows (timepoints that wrap like a negative Python index). */
+F2_API int f2_gather_index(const float* src, int n_channels, const int64_t* idx, int64_t n_idx, float* out, void* stream);
+/* Dense framing of Evaluating.py:70-78: frame i = env_t rows i + k*step, k < dots, for
+ * i0 <= i < i1; normalize != 0 applies Training.normalizeInput (Training.py:13-28) per frame
+ * and sets *bad_flag (device int) when a frame has a value <= 0 (the reference raises). */
+F2_API int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int64_t i0, int64_t i1, int normalize,
+                    void* out, int out_dtype, int* bad_flag, void* stream);
+
+/* butter(1, cutoff_hz/8000, 'low') as used by lowPassFilter (EnvelopeExtraction.py:47):
+ * y[t] = b0*(x[t]+x[t-1]) - a1*y[t-1].  Host-only helper. */
+F2_API int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F2CNN_B200_H */

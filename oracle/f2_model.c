@@ -1,0 +1,145 @@
+/*
+ * f2_model.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A scalar float32 CPU model of the arithmetic the CUDA kernels perform (streaming
+ * ring formulation of the padded-FFT Hilbert envelope, delta-form biquads, truncated
+ * warm-ups).  It exists to study precision and warm-up lengths offline, where there
+ * is no GPU; it is not the oracle (that is f2_oracle.c, float64, the reference's
+ * algorithm) and it is not a product path.
+ *
+ * Per channel (parameters prepared in float64, rounded once to float32):
+ *   cq = B2, cy = 1 + B1 + B2   (pole pair, "delta" form: q = y[t]-y[t-1])
+ *   a0 = A0/g^(1/4), a1[k] = A1k/g^(1/4)   (gain folded per stage)
+ * Stage update (input u[t], up = u[t-1]):
+ *   in = a0*u + a1*up (+ e*G[t] on the imaginary path)
+ *   q  = cq*q + in ; q = q - cy*y ; y = y + q
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    float cq[4], cy[4], a0, a1[4], s[4]; /* s[k] = a0 + a1[k] (form 1) */
+} chan_t;
+
+/* Round c to float32 per stage so that the four stage values sum to 4*c as closely as
+ * the float32 lattice allows: the first-order response error of the cascade depends
+ * only on the sum of the per-stage denominator errors (shared poles). */
+static int g_dither = 1;
+void f2m_set_dither(int d) { g_dither = d; }
+static void dither4(double c, float *out)
+{
+    float r = (float)c;
+    if (!g_dither) { for (int k = 0; k < 4; ++k) out[k] = r; return; }
+    float lo = ((double)r <= c) ? r : nextafterf(r, -INFINITY);
+    float hi = nextafterf(lo, INFINITY);
+    double frac = (c - (double)lo) / ((double)hi - (double)lo);
+    int m = (int)floor(4.0 * frac + 0.5);
+    for (int k = 0; k < 4; ++k) out[k] = (k < m) ? hi : lo;
+}
+
+static void prep(const double *k10, chan_t *p)
+{
+    double gq = pow(k10[9], 0.25);
+    double a0 = k10[0] / gq;
+    dither4(k10[8], p->cq);
+    dither4(1.0 + k10[7] + k10[8], p->cy);
+    p->a0 = (float)a0;
+    for (int k = 0; k < 4; ++k) {
+        p->a1[k] = (float)(k10[1 + k] / gq);
+        p->s[k] = (float)((k10[0] + k10[1 + k]) / gq);
+    }
+}
+
+/* one cascade step on one path.  y[4], q[4] states; u = input sample, up = previous
+ * input; inj[k] = injection for stage k (0 on the real path).  form 0: in = a0*u+a1*up;
+ * form 1: in = a0*(u-up) + s*up with stage>=2 using q of the previous stage. */
+static inline float cascade_step(const chan_t *p, float *y, float *q, float u, float up, const float *inj, int form)
+{
+    float du = u - up;
+    for (int k = 0; k < 4; ++k) {
+        float in;
+        if (form == 0) in = fmaf(p->a0, u, p->a1[k] * up);
+        else in = fmaf(p->a0, du, p->s[k] * up);
+        if (inj) in = in + inj[k];
+        float yold = y[k];
+        float qn = fmaf(p->cq[k], q[k], in);
+        qn = fmaf(-p->cy[k], yold, qn);
+        float yn = yold + qn;
+        q[k] = qn;
+        y[k] = yn;
+        up = yold; /* next stage: previous input = this stage's previous output */
+        u = yn;
+        du = qn;
+    }
+    return y[3];
+}
+
+/* xf/xi: ring arrays of length N2 (x zero-padded; Im of its circular analytic signal).
+ * G: ring array, G[t] = h[(t-n) mod N2] if (t-n) odd else h[(t-n-1) mod N2].
+ * Outputs (C,n) float32 row-major; either may be NULL. */
+void f2m_run(const float *xf, const float *xi, const float *G, int64_t n, int64_t N2, const double *coefs, int C,
+             int lpf, double lp_b0, double lp_a1, int64_t W, int64_t We, int form, float *out_gfb, float *out_env)
+{
+    const float k_lp = (float)(-lp_a1), b0_lp = (float)lp_b0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < C; ++c) {
+        chan_t p;
+        prep(coefs + (size_t)c * 10, &p);
+        /* E phase: real path over the last We samples from zero state -> edge residuals */
+        float y[4] = { 0, 0, 0, 0 }, q[4] = { 0, 0, 0, 0 };
+        int64_t t0 = n - We > 0 ? n - We : 0;
+        float up = t0 > 0 ? xf[t0 - 1] : 0.0f;
+        for (int64_t t = t0; t < n; ++t) { cascade_step(&p, y, q, xf[t], up, NULL, form); up = xf[t]; }
+        /* e0[k] at ring index n, e1[k] at n+1:
+         *   e0 = b1*y[n-1] + b2*y[n-2] - a1k*yprev_stage[n-1] = (cy-1)*y - cq*q - a1k*u
+         *   e1 = b2*y[n-1] = cq*y */
+        float e0[4], e1[4];
+        for (int k = 0; k < 4; ++k) {
+            float uprev = (k == 0) ? (n > 0 ? xf[n - 1] : 0.0f) : y[k - 1];
+            e0[k] = fmaf(p.cy[k] - 1.0f, y[k], -p.cq[k] * q[k]) - p.a1[k] * uprev;
+            e1[k] = p.cq[k] * y[k];
+        }
+        /* imaginary path: periodic steady state by a W-sample warm-up on the ring */
+        float vy[4] = { 0, 0, 0, 0 }, vq[4] = { 0, 0, 0, 0 };
+        float inj[4];
+        float vup = 0.0f;
+        if (N2 > 2) {
+            int64_t r = ((-W) % N2 + N2) % N2;
+            vup = xi[(r - 1 + N2) % N2];
+            for (int64_t t = -W; t < 0; ++t) {
+                int64_t rr = ((t % N2) + N2) % N2;
+                int odd = (int)(((t - n) % 2 + 2) % 2);
+                for (int k = 0; k < 4; ++k) inj[k] = (odd ? e0[k] : e1[k]) * G[rr];
+                cascade_step(&p, vy, vq, xi[rr], vup, inj, form);
+                vup = xi[rr];
+            }
+        }
+        /* main pass */
+        for (int k = 0; k < 4; ++k) { y[k] = 0; q[k] = 0; }
+        up = 0.0f;
+        float l = 0.0f, eprev = 0.0f;
+        for (int64_t t = 0; t < n; ++t) {
+            float yr = cascade_step(&p, y, q, xf[t], up, NULL, form);
+            up = xf[t];
+            float yi = 0.0f;
+            if (N2 > 2) {
+                int odd = (int)(((t - n) % 2 + 2) % 2);
+                for (int k = 0; k < 4; ++k) inj[k] = (odd ? e0[k] : e1[k]) * G[t];
+                yi = cascade_step(&p, vy, vq, xi[t], vup, inj, form);
+                vup = xi[t];
+            }
+            if (out_gfb) out_gfb[(size_t)c * n + t] = yr;
+            if (out_env) {
+                float e = sqrtf(fmaf(yr, yr, yi * yi));
+                if (lpf) {
+                    /* l~ = (e + eprev) + k*l~ ; out = b0*l~ */
+                    l = fmaf(k_lp, l, e + eprev);
+                    eprev = e;
+                    out_env[(size_t)c * n + t] = b0_lp * l;
+                } else out_env[(size_t)c * n + t] = e;
+            }
+        }
+    }
+}
