@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- channel-samples/s of the F2CNN feature-extraction hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host threads)
+
+Workload (BASELINE.json configs[1]): a synthetic
+TIMIT-TRAIN-sized corpus -- 4620 utterances, lengths U(32000, 64000) samples at 16 kHz,
+int16 white noise -- through the 128-channel ERB gammatone filterbank, the ENV1 envelope
+with the 50 Hz low-pass and the window gather on the full label grid, producing the
+(N, 11, 128) float32 input tensor.  One step = one pass of that path over the whole corpus
+shard of a rank.  Multi-GPU: utterances are independent, every rank processes its own
+corpus-sized shard with no collective (weak scaling); value = channel-samples of all ranks /
+max-over-ranks device time.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same metric
+through api.features_to_windows-style staging with HOST buffers -- pinned int16 waves H2D and
+the float32 input tensor D2H inside the timed region.  `roofline`: the fused kernel against
+the FP32 FMA peak (80 FLOP per channel-sample), timed with CUDA events on its
+own stream inside the timed region.  `cpu_baseline`: the float64 oracle port (the reference's
+algorithm restated in C, reference Python cannot travel to the GPU box) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS, C, LOW, CUTOFF, RADIUS, STEP = 16000, 128, 100, 50, 5, 160
+N_UTTS, LEN_LO, LEN_HI = 4620, 32000, 64000
+FLOP_PER_CS = 80.0  # 40 FP32 FMA per channel-sample: filterbank + envelope + LPF
+KERNELS_PER_STEP = 9  # pack, fft cols/rows fwd, mask, fft cols/rows inv, finish, fused, gather
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances per rank (default: the config's 4620)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---- clocks --------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        load = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] if power else sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU arm -------------------------------------------------------------------------------
+def cpu_arm(coefs, lengths, seed, seconds, steps=1, warmup=0):
+    """Time the oracle port (erb_filterbank -> ExtractEnvelopeFromMatrix(True,50) -> window
+    gather, float64, in memory) on a bounded sample of the corpus with all host threads."""
+    from f2cnn_b200 import synth
+    from oracle import oracle as orc
+    orc.lib()
+    cores = orc.num_threads()
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(len(lengths))
+
+    def run(idx):
+        n = int(lengths[idx])
+        w = synth.white_noise_i16(n, seed=10_000 + int(idx))
+        t = time.perf_counter()
+        orc.utterance(w, coefs, True, CUTOFF, synth.label_grid(n), RADIUS, STEP)
+        return time.perf_counter() - t, n
+
+    dt, n0 = run(order[0])  # calibration (also warms the twiddle / page cache)
+    per_step = max(2, min(len(order), int(seconds / max(dt, 1e-3) / max(steps, 1))))
+    for _ in range(warmup):
+        run(order[0])
+    total_t, total_n = 0.0, 0
+    pos = 0
+    step_rates = []
+    for _ in range(steps):
+        st, sn = 0.0, 0
+        for _ in range(per_step):
+            d, n = run(order[pos % len(order)])
+            pos += 1
+            st += d
+            sn += n
+        step_rates.append(C * sn / st)
+        total_t += st
+        total_n += sn
+    return {"value": C * total_n / total_t, "unit": "channel-samples/s", "cores": cores, "kind": "port",
+            "sample": "%d utterances (%d samples) of the corpus per step x %d steps, float64 C port of the "
+                      "reference algorithm, OpenMP over channels, in memory" % (per_step, total_n // max(steps, 1),
+                                                                                steps),
+            "seconds": total_t}, total_t / max(steps, 1)
+
+
+def main():
+    args = parse()
+    rank, local_rank, world = dist_env()
+    from f2cnn_b200 import synth
+    from f2cnn_b200.gammatone import filters
+    coefs = filters.make_erb_filters(FS, filters.centre_freqs(FS, C, LOW))
+    config = {"workload": "synthetic TIMIT-TRAIN-sized corpus: %d utterances x U(%d,%d) samples @16 kHz int16, "
+                          "%d-ch ERB gammatone -> ENV1 (LPF %d Hz) -> (N,11,%d) float32 windows on the full label "
+                          "grid" % (args.utts, LEN_LO, LEN_HI, C, CUTOFF, C),
+              "utterances_per_gpu": args.utts, "channels": C, "lpf_hz": CUTOFF,
+              "l2": "inputs larger than L2 (rings %.1f GB per pass), no flush needed" % (args.utts * 65536 * 16 / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        lengths = synth.corpus_lengths(args.utts, LEN_LO, LEN_HI, seed=1)
+        cb, ms = cpu_arm(coefs, lengths, 1, args.cpu_seconds * 4, steps=args.steps, warmup=min(args.warmup, 1))
+        print(json.dumps({"impl": "reference", "metric": "channel-samples/sec (filterbank+envelope)",
+                          "value": cb["value"], "unit": "channel-samples/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": "channel-samples/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from f2cnn_b200 import engine
+
+    lengths = synth.corpus_lengths(args.utts, LEN_LO, LEN_HI, seed=1 + rank)
+    flat, offsets = synth.corpus_waves_i16(lengths, seed=1 + rank)
+    total_samples = int(offsets[-1])
+    cs_per_step = float(C) * total_samples
+
+    plan = engine.plan_for(coefs, local_rank)
+    batch = plan.batch(lengths, step=STEP, phase=0)
+    # label grid: centres 800 + 160k, k < int(n/160 - 12): first frame of window k is frame k
+    nwin = np.maximum((lengths / STEP - (2 * RADIUS + 1) - 1).astype(np.int64), 0)
+    base = np.concatenate([batch.frame_offsets[u] + np.arange(nwin[u], dtype=np.int64) for u in range(len(lengths))])
+    n_windows = int(base.shape[0])
+    dots = 2 * RADIUS + 1
+
+    wave_host = torch.from_numpy(flat).pin_memory()
+    wave_dev = wave_host.to(dev)
+    base_dev = torch.from_numpy(base).to(dev)
+    dec = torch.empty((batch.total_frames, C), dtype=torch.float32, device=dev)
+    windows = torch.empty((n_windows, dots, C), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(events=None):
+        batch.run(wave_dev, lpf=True, cutoff=CUTOFF, out={"dec": dec}, fused_events=events)
+        engine.gather_windows(dec, base_dev, dots, 1, out=windows)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(engine.DeviceEvent(), engine.DeviceEvent()) for _ in range(args.steps)]
+    t_start, t_stop = engine.DeviceEvent(), engine.DeviceEvent()
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        step(ev[i])
+    t_stop.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_ms(t_stop)
+    fused_ms = float(np.mean([a.elapsed_ms(b) for a, b in ev]))
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * cs_per_step / (ms_step * 1e-3)
+
+    # ---- e2e: host int16 waves in, host float32 input tensor out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        try:
+            out_host = torch.empty((n_windows, dots, C), dtype=torch.float32, pin_memory=True)
+        except RuntimeError:
+            out_host = torch.empty((n_windows, dots, C), dtype=torch.float32)
+
+        def e2e_step():
+            wave_dev.copy_(wave_host, non_blocking=True)
+            step()
+            out_host.copy_(windows, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        k = max(2, min(args.steps, 5))
+        a, b = engine.DeviceEvent(), engine.DeviceEvent()
+        a.record()
+        for _ in range(k):
+            e2e_step()
+        b.record()
+        barrier()
+        ms_e2e = a.elapsed_ms(b)
+        if world > 1:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        e2e = {"value": world * cs_per_step / (ms_e2e / k * 1e-3), "unit": "channel-samples/s",
+               "h2d_bytes_per_step": int(wave_host.numel() * 2), "d2h_bytes_per_step": int(out_host.numel() * 4),
+               "ms_per_step": ms_e2e / k, "pinned_output": bool(out_host.is_pinned())}
+        del out_host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    fma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s, nominal FP32 FMA at max clock
+    achieved = FLOP_PER_CS * cs_per_step / (fused_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32_fma", "kernel": "fused_kernel", "achieved": achieved, "peak": fma_peak,
+                "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": None,
+                "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 entry); "
+                               "tools/fma_peak.cu measured 73.8 TFLOP/s sustained (FFMA2) on this pool",
+                "kernel_ms": fused_ms, "kernel_share_of_step": fused_ms / ms_step,
+                "algorithmic_flop_per_channel_sample": FLOP_PER_CS,
+                "hbm": {"algorithmic_bytes_per_channel_sample": 12.0 / C + 4.0 / STEP,
+                        "achieved_GBps": (12.0 / C + 4.0 / STEP) * cs_per_step / (fused_ms * 1e-3) / 1e9,
+                        "peak_GBps": peaks.get("hbm_gbs")}}
+    cpu = None
+    if not args.no_cpu:
+        cpu, _ = cpu_arm(coefs, lengths, 1, args.cpu_seconds)
+    out = {"metric": "channel-samples/sec (filterbank+envelope)", "value": value, "unit": "channel-samples/s",
+           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps,
+           "roofline": roofline, "cpu_baseline": cpu, "windows_per_step": n_windows * world}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libf2cnn_b200.so")
 
 F2_OK = 0
 F2_I16, F2_F32, F2_F64 = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class F2Error(RuntimeError):
@@ -32,6 +32,8 @@ class RunArgs(ctypes.Structure):
         ("env_dtype", ctypes.c_int),
         ("env_t", ctypes.c_void_p),
         ("dec", ctypes.c_void_p),
+        ("ev_fused_start", ctypes.c_void_p),
+        ("ev_fused_stop", ctypes.c_void_p),
     ]
 
 
@@ -69,6 +71,11 @@ SIGNATURES = {
     "f2_dense_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                        ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "f2_event_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
+    "f2_event_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "f2_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "f2_event_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "f2_event_elapsed_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "f2_lowpass_coefficients": (ctypes.c_int, [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(ctypes.c_double)]),
 }

@@ -101,7 +101,7 @@ struct f2_batch {
 extern "C" {
 
 const char* f2_last_error(void) { return g_err; }
-int f2_abi_version(void) { return 1; }
+int f2_abi_version(void) { return 2; }
 
 int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1) {
     if (!b0 || !a1 || !(cutoff_hz > 0.0) || !(cutoff_hz < 8000.0))
@@ -411,7 +411,9 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     fp.w_casc = plan->w_casc;
     // low-pass warm-up of a mid-signal chunk: |a1|^W < 1e-7
     fp.w_lpf = a->lpf ? round_up_tile(log(1e-7) / log(-a1)) : 0;
+    if (a->ev_fused_start) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_start, stream));
     F2_CUDA(f2::launch_fused(fp, (int)b->n_items, stream));
+    if (a->ev_fused_stop) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_stop, stream));
 
     if (a->gfb)
         F2_CUDA(f2::launch_transpose_convert(b->d_utts, b->n_utts, b->max_n, gfb_t, a->gfb, a->gfb_dtype, plan->C,
@@ -505,6 +507,32 @@ int f2_envelope_rows(f2_plan* plan, const void* matrix, int dtype, int64_t rows,
     F2_CUDA(f2::launch_prep(pp, hp, stream));
     F2_CUDA(f2::launch_rows_envelope(d_rows, (int)r.rows_pad, xz, lpf ? 1 : 0, (float)(-a1), (float)b0, out, out_dtype,
                                      stream));
+    return F2_OK;
+}
+
+// ---- events -------------------------------------------------------------------------------
+int f2_event_create(void** event) {
+    if (!event) return fail(F2_ERR_INVALID, "null event pointer");
+    cudaEvent_t e;
+    F2_CUDA(cudaEventCreate(&e));
+    *event = (void*)e;
+    return F2_OK;
+}
+int f2_event_destroy(void* event) {
+    if (event) F2_CUDA(cudaEventDestroy((cudaEvent_t)event));
+    return F2_OK;
+}
+int f2_event_record(void* event, void* stream) {
+    F2_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return F2_OK;
+}
+int f2_event_synchronize(void* event) {
+    F2_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+    return F2_OK;
+}
+int f2_event_elapsed_ms(void* start, void* stop, float* ms) {
+    if (!ms) return fail(F2_ERR_INVALID, "null ms pointer");
+    F2_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
     return F2_OK;
 }
 

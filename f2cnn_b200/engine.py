@@ -56,13 +56,13 @@ class Plan:
         self._ws = None
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h is not None and h.value:
-            try:
+        try:
+            h = getattr(self, "_h", None)
+            if h is not None and h.value:
                 _native.lib().f2_plan_destroy(h)
-            except Exception:
-                pass
-            self._h = ctypes.c_void_p()
+                self._h = None
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     def set_warmup(self, w_imag=0, w_edge=0, w_casc=0):
         check(_native.lib().f2_plan_set_warmup(self._h, int(w_imag), int(w_edge), int(w_casc)))
@@ -117,19 +117,19 @@ class Batch:
         np.cumsum(self.lengths, out=self.sample_offsets[1:])
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h is not None and h.value:
-            try:
+        try:
+            h = getattr(self, "_h", None)
+            if h is not None and h.value:
                 _native.lib().f2_batch_destroy(h)
-            except Exception:
-                pass
-            self._h = ctypes.c_void_p()
+                self._h = None
+        except Exception:
+            pass
 
     def workspace_bytes(self, want_full_gfb=False, want_full_env=False):
         return int(_native.lib().f2_batch_workspace_bytes(self._h, int(want_full_gfb), int(want_full_env)))
 
     def run(self, wave_dev, lpf=False, cutoff=100, gfb=None, env=None, env_t=False, dec=False, stream=None,
-            out=None):
+            out=None, fused_events=None):
         """wave_dev: flat device tensor (int16/float32/float64) of total_samples.
         gfb/env: None or torch.float64/float32 -> (C*total_samples,) reference-layout blocks;
         env_t: time-major [total_samples, C] float32; dec: [total_frames, C] float32.
@@ -161,10 +161,39 @@ class Batch:
         a.env_dtype = _T2F2[e.dtype] if e is not None else F2_F64
         a.env_t = res["env_t"].data_ptr() if "env_t" in res else None
         a.dec = res["dec"].data_ptr() if "dec" in res else None
+        if fused_events is not None:  # (DeviceEvent, DeviceEvent) around the fused kernel
+            a.ev_fused_start, a.ev_fused_stop = fused_events[0].handle, fused_events[1].handle
         need = self.workspace_bytes(g is not None, e is not None and "env_t" not in res)
         ws = plan.workspace(need)
         check(_native.lib().f2_batch_run(self._h, ctypes.byref(a), _ptr(ws), ws.numel(), _stream_ptr(stream)))
         return res
+
+
+class DeviceEvent:
+    """cudaEvent_t owned through the C ABI (recorded on the stream the kernels run on)."""
+
+    def __init__(self):
+        self.handle = ctypes.c_void_p()
+        check(_native.lib().f2_event_create(ctypes.byref(self.handle)))
+
+    def record(self, stream=None):
+        check(_native.lib().f2_event_record(self.handle, _stream_ptr(stream)))
+
+    def synchronize(self):
+        check(_native.lib().f2_event_synchronize(self.handle))
+
+    def elapsed_ms(self, stop):
+        ms = ctypes.c_float()
+        check(_native.lib().f2_event_elapsed_ms(self.handle, stop.handle, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def __del__(self):
+        try:
+            if self.handle is not None and self.handle.value:
+                _native.lib().f2_event_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 # ---- windowing helpers ---------------------------------------------------------------------

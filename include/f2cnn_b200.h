@@ -92,6 +92,8 @@ typedef struct f2_run_args {
     int env_dtype;
     float* env_t;     /* out, nullable: envelope time-major [sum n][C] float32             */
     float* dec;       /* out, nullable: decimated envelope frames [total_frames][C] float32 */
+    void* ev_fused_start; /* nullable cudaEvent_t recorded on `stream` right before ...     */
+    void* ev_fused_stop;  /* ... and right after the fused kernel (for roofline timing)     */
 } f2_run_args;
 
 /* Replaces, fused: filters.erb_filterbank (gammatone/filters.py:195-239),
@@ -120,6 +122,13 @@ F2_API int f2_gather_index(const float* src, int n_channels, const int64_t* idx,
  * and sets *bad_flag (device int) when a frame has a value <= 0 (the reference raises). */
 F2_API int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int64_t i0, int64_t i1, int normalize,
                     void* out, int out_dtype, int* bad_flag, void* stream);
+
+/* ---- CUDA event helpers so that a host without a CUDA binding can time on the device ----- */
+F2_API int f2_event_create(void** event);
+F2_API int f2_event_destroy(void* event);
+F2_API int f2_event_record(void* event, void* stream);
+F2_API int f2_event_synchronize(void* event);
+F2_API int f2_event_elapsed_ms(void* start, void* stop, float* ms);
 
 /* butter(1, cutoff_hz/8000, 'low') as used by lowPassFilter (EnvelopeExtraction.py:47):
  * y[t] = b0*(x[t]+x[t-1]) - a1*y[t-1].  Host-only helper. */
