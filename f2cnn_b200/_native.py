@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libf2cnn_b200.so")
 
 F2_OK = 0
 F2_I16, F2_F32, F2_F64 = 0, 1, 2
-ABI_VERSION = 2
+F2_ROWS_ENVELOPE, F2_ROWS_HILBERT, F2_ROWS_LOWPASS = 0, 1, 2
+ABI_VERSION = 3
 
 
 class F2Error(RuntimeError):
@@ -64,6 +65,11 @@ SIGNATURES = {
     "f2_envelope_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "f2_rows_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "f2_gather_windows_cn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "f2_gather_windows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                          ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "f2_gather_index": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,

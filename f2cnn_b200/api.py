@@ -91,6 +91,41 @@ def extract_envelope_from_matrix(matrix, LPF=False, CUTOFF=100):
     return _to_host(out)
 
 
+def _rows_op(matrix, op, lpf, cutoff):
+    m = np.asarray(matrix)
+    if m.dtype not in (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int16)):
+        m = m.astype(np.float64)
+    m = np.ascontiguousarray(m)
+    if m.shape[1] == 0:
+        raise ValueError("N must be positive.")
+    plan = engine.any_plan()
+    out = plan.envelope_rows(_to_device(m, plan.device), lpf, cutoff, out_dtype=torch.float64, op=op)
+    return _to_host(out)
+
+
+def hilbert_imag_rows(matrix):
+    """Imaginary part of paddedHilbert(row) for every row (EnvelopeExtraction.py:20-36)."""
+    return _rows_op(matrix, 1, False, 100)
+
+
+def lowpass_rows(matrix, freq):
+    """lowPassFilter(row, freq) for every row (EnvelopeExtraction.py:39-48)."""
+    return _rows_op(matrix, 2, True, freq)
+
+
+def gather_windows_from_matrix(envelopes, timepoints, radius=5, step=160):
+    """InputGenerator.py:73-80 on a loaded (C, n) envelope matrix -> (m, 2R+1, C) float32."""
+    env = np.ascontiguousarray(envelopes)
+    if env.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        env = env.astype(np.float64)
+    C, n = env.shape
+    idx = window_indices(n, timepoints, radius, step)
+    plan = engine.any_plan()
+    out = engine.gather_windows_cn(_to_device(env, plan.device),
+                                   _to_device(np.ascontiguousarray(idx.reshape(-1)), plan.device))
+    return _to_host(out).reshape(idx.shape[0], 2 * radius + 1, C)
+
+
 def window_indices(n, centers, radius, step):
     """Sample indices read by InputGenerator.py:76 for one file, with Python list
     semantics: a negative index wraps once, anything else out of range is an IndexError."""

@@ -101,7 +101,7 @@ struct f2_batch {
 extern "C" {
 
 const char* f2_last_error(void) { return g_err; }
-int f2_abi_version(void) { return 2; }
+int f2_abi_version(void) { return 3; }
 
 int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1) {
     if (!b0 || !a1 || !(cutoff_hz > 0.0) || !(cutoff_hz < 8000.0))
@@ -136,9 +136,10 @@ int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** ou
         const double b1 = B1 / B0, b2 = B2 / B0;
         if (!(b2 > 0.0 && b2 < 1.0) || !(fabs(b1) < 1.0 + b2))
             return fail(F2_ERR_UNSUPPORTED, "channel %d: poles are not a stable complex pair", c);
-        const double gq = pow(gain, 0.25);
-        par[(size_t)f2::P_A0 * c_pad + c] = (float)(A0 / B0 / gq);
-        for (int s = 0; s < 4; ++s) par[(size_t)(f2::P_A1 + s) * c_pad + c] = (float)(k[1 + s] / B0 / gq);
+        if (!(A0 != 0.0)) return fail(F2_ERR_INVALID, "channel %d: A0 == 0", c);
+        const double a0n = A0 / B0;
+        par[(size_t)f2::P_G4 * c_pad + c] = (float)(a0n * a0n * a0n * a0n / gain);
+        for (int s = 0; s < 4; ++s) par[(size_t)(f2::P_Z + s) * c_pad + c] = (float)(k[1 + s] / A0);
         float cq[4], ncy[4];
         dither4(b2, cq);
         dither4(-(1.0 + b1 + b2), ncy);
@@ -465,7 +466,14 @@ size_t f2_envelope_rows_workspace_bytes(int64_t rows, int64_t n) {
 int f2_envelope_rows(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64_t n, int lpf,
                      double cutoff_hz, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
                      void* stream_) {
-    if (!plan || rows < 0 || n < 0) return fail(F2_ERR_INVALID, "f2_envelope_rows: bad arguments");
+    return f2_rows_op(plan, matrix, dtype, rows, n, F2_ROWS_ENVELOPE, lpf, cutoff_hz, out, out_dtype, workspace,
+                      workspace_bytes, stream_);
+}
+
+int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64_t n, int op, int lpf,
+               double cutoff_hz, void* out, int out_dtype, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!plan || rows < 0 || n < 0 || op < F2_ROWS_ENVELOPE || op > F2_ROWS_LOWPASS)
+        return fail(F2_ERR_INVALID, "f2_rows_op: bad arguments");
     if (rows == 0 || n == 0) return F2_OK;
     if (!matrix || !out || dtype < F2_I16 || dtype > F2_F64 || (out_dtype != F2_F32 && out_dtype != F2_F64))
         return fail(F2_ERR_INVALID, "f2_envelope_rows: pointer/dtype");
@@ -500,13 +508,13 @@ int f2_envelope_rows(f2_plan* plan, const void* matrix, int dtype, int64_t rows,
     pp.Z = Z;
     pp.xz = xz;
     pp.G = nullptr;
-    pp.hilbert = 1;
+    pp.hilbert = op == F2_ROWS_LOWPASS ? 0 : 1;
     f2::HostPrepInfo hp;
     hp.n_utts = (int)rows;
     hp.min_log2N2 = hp.max_log2N2 = r.lg;
     F2_CUDA(f2::launch_prep(pp, hp, stream));
-    F2_CUDA(f2::launch_rows_envelope(d_rows, (int)r.rows_pad, xz, lpf ? 1 : 0, (float)(-a1), (float)b0, out, out_dtype,
-                                     stream));
+    F2_CUDA(f2::launch_rows_envelope(d_rows, (int)r.rows_pad, xz, op, lpf ? 1 : 0, (float)(-a1), (float)b0, out,
+                                     out_dtype, stream));
     return F2_OK;
 }
 
@@ -552,6 +560,15 @@ int f2_gather_index(const float* src, int n_channels, const int64_t* idx, int64_
     if (n_idx == 0) return F2_OK;
     if (!src || !idx || !out || n_channels <= 0 || n_idx < 0) return fail(F2_ERR_INVALID, "f2_gather_index: bad arguments");
     F2_CUDA(f2::launch_gather_index(src, (const long long*)idx, n_idx, n_channels, out, (cudaStream_t)stream));
+    return F2_OK;
+}
+
+int f2_gather_windows_cn(const void* env, int dtype, int n_channels, int64_t n, const int64_t* idx, int64_t n_idx,
+                         float* out, void* stream) {
+    if (n_idx == 0) return F2_OK;
+    if (!env || !idx || !out || n_channels <= 0 || n <= 0 || n_idx < 0 || (dtype != F2_F32 && dtype != F2_F64))
+        return fail(F2_ERR_INVALID, "f2_gather_windows_cn: bad arguments");
+    F2_CUDA(f2::launch_gather_cn(env, dtype, n_channels, n, (const long long*)idx, n_idx, out, (cudaStream_t)stream));
     return F2_OK;
 }
 

@@ -21,11 +21,11 @@ constexpr int kRingAlign = 256;   // ring allocations are multiples of this many
 constexpr int kNumChanPar = 16;   // floats per channel in the parameter block
 
 // Per-channel parameter block, parameter-major: par[i * c_pad + c].
-//   0      a0      = A0 / gain^(1/4)                      (filters.py:148,174-182)
-//   1..4   a1[k]   = A1k / gain^(1/4)                     (filters.py:167-170)
+//   0      g4      = A0^4 / gain: output scale of the cascade (filters.py:148,174-182,237)
+//   1..4   z[k]    = A1k / A0: the stage's zero           (filters.py:167-170)
 //   5..8   cq[k]   = B2 rounded per stage (dithered)      (filters.py:152)
 //   9..12  ncy[k]  = -(1 + B1 + B2) rounded per stage     (filters.py:151-152)
-enum ChanPar { P_A0 = 0, P_A1 = 1, P_CQ = 5, P_NCY = 9 };
+enum ChanPar { P_G4 = 0, P_Z = 1, P_CQ = 5, P_NCY = 9 };
 
 // One utterance (or one matrix row for the stand-alone envelope path).
 struct UttDesc {

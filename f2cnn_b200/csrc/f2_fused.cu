@@ -20,8 +20,13 @@
 // packed FFMA2/FADD2 instructions.  Each biquad is in "delta" form (state y[t-1] and
 // q = y[t-1]-y[t-2]), which keeps float32 coefficient quantisation harmless for poles
 // 0.039 rad from z=1:
-//     in = a0*u[t] + a1k*u[t-1]  (+ e_k*G[t] on the imaginary half)
+//     in = u[t] + z_k*u[t-1]     (+ e_k*G[t] on the imaginary half)      z_k = A1k/A0
 //     q  = cq*q + in - cy*y ;  y = y + q
+// Every stage is computed WITHOUT its common numerator gain a0 = A0/gain^(1/4): stage k holds
+// y_k / a0^k, and the single factor a0^4 = A0^4/gain is applied where a value leaves the
+// kernel (folded into the low-pass b0 when the low-pass is on).  That leaves 4 packed + 1
+// scalar FMA-pipe instructions per stage: 40 FMA-pipe lane-cycles per channel-sample for
+// filterbank + envelope + low-pass, exactly the algorithmic count of SURVEY.md section 8d.
 // The imaginary half solves the N2-periodic ring equation that the reference's
 // zero-padded FFT Hilbert transform implies: e_k are the residuals of the
 // zero-padded real cascade at ring positions n and n+1, G[t] is the circular Hilbert
@@ -37,10 +42,10 @@
 namespace f2 {
 
 struct Coef {
-    float2 a0;
-    float2 a1[4];
-    float2 cq[4];
-    float2 ncy[4];
+    float2 z[4];    // A1k/A0 (the stage's zero), broadcast to both halves
+    float2 cq[4];   // B2 per stage
+    float2 ncy[4];  // -(1+B1+B2) per stage
+    float g4;       // A0^4/gain: the cascade's output scale
 };
 
 struct State {
@@ -69,7 +74,7 @@ __device__ __forceinline__ float2 cascade(const Coef& k, State& s, float2 u, flo
     s.up = u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 in = __ffma2_rn(k.a0, u, __fmul2_rn(k.a1[i], up));
+        float2 in = __ffma2_rn(k.z[i], up, u);
         in.y = fmaf(e[i], g, in.y);
         const float2 yo = s.y[i];
         float2 qn = __ffma2_rn(k.cq[i], s.q[i], in);
@@ -89,7 +94,7 @@ __device__ __forceinline__ void cascade_real(const Coef& k, State& s, float u) {
     s.up.x = u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float in = fmaf(k.a0.x, u, k.a1[i].x * up);
+        const float in = fmaf(k.z[i].x, up, u);
         const float yo = s.y[i].x;
         float qn = fmaf(k.cq[i].x, s.q[i].x, in);
         qn = fmaf(k.ncy[i].x, yo, qn);
@@ -102,6 +107,8 @@ __device__ __forceinline__ void cascade_real(const Coef& k, State& s, float u) {
 }
 
 // ENV: 0 = cascade only, 1 = magnitude, 2 = magnitude + low-pass.
+// OUT: 0 = nothing leaves the kernel (warm-up), 1 = decimated frames only, 2 = full-rate
+//      time-major stores (and decimated frames when asked).
 struct OutCtx {
     float* gfb;     // points at sample t of this thread's channel (or null)
     float* env;
@@ -109,20 +116,23 @@ struct OutCtx {
     int next_dec;   // time index of the next decimated frame
     int step;
     size_t C;
+    float env_scale;  // g4 (no low-pass) or g4*b0 (low-pass): applied when a value is stored
 };
 
+// Unscaled envelope sample: |y| (ENV 1) or the low-pass state (ENV 2); the caller multiplies
+// by OutCtx::env_scale only for the samples that are actually stored.
 template <int ENV>
 __device__ __forceinline__ float envelope(const FusedParams& p, State& s, float2 y) {
     float e = fast_sqrt(fmaf(y.x, y.x, y.y * y.y));
     if (ENV == 2) {
         s.l = fmaf(p.lp_k, s.l, e + s.eprev);
         s.eprev = e;
-        e = p.lp_b0 * s.l;
+        e = s.l;
     }
     return e;
 }
 
-template <int ENV, bool OUT, bool ZEROX>
+template <int ENV, int OUT, bool ZEROX>
 __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, State& s, const float (&ee)[4],
                                          const float (&eo)[4], const float2* __restrict__ sxz,
                                          const float* __restrict__ sg, int t, int cnt, bool active, OutCtx& o) {
@@ -152,24 +162,24 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             const float2 u = make_float2(ZEROX ? 0.f : xv[2 * j], xv[2 * j + 1]);
             const float2 y = (j & 1) ? cascade(k, s, u, gv[j], eo) : cascade(k, s, u, gv[j], ee);
             if (ENV > 0) ev[j] = envelope<ENV>(p, s, y);
-            if (OUT) {
-                if (o.gfb && active) __stcs(o.gfb + (size_t)j * o.C, y.x);
-                if (ENV > 0 && o.env && active) __stcs(o.env + (size_t)j * o.C, ev[j]);
+            if (OUT == 2) {
+                if (o.gfb && active) __stcs(o.gfb + (size_t)j * o.C, k.g4 * y.x);
+                if (ENV > 0 && o.env && active) __stcs(o.env + (size_t)j * o.C, o.env_scale * ev[j]);
             }
         }
-        if (OUT) {
+        if (OUT == 2) {
             if (o.gfb) o.gfb += 8 * o.C;
             if (o.env) o.env += 8 * o.C;
-            if (ENV > 0 && o.dec) {
-                while (o.next_dec < t + i + 8) {
-                    const int r = o.next_dec - (t + i);
-                    float v = ev[0];
+        }
+        if (OUT > 0 && ENV > 0 && o.dec) {
+            while (o.next_dec < t + i + 8) {
+                const int r = o.next_dec - (t + i);
+                float v = ev[0];
 #pragma unroll
-                    for (int j = 1; j < 8; ++j) v = (r == j) ? ev[j] : v;
-                    if (active) __stcs(o.dec, v);
-                    o.dec += o.C;
-                    o.next_dec += o.step;
-                }
+                for (int j = 1; j < 8; ++j) v = (r == j) ? ev[j] : v;
+                if (active) __stcs(o.dec, o.env_scale * v);
+                o.dec += o.C;
+                o.next_dec += o.step;
             }
         }
     }
@@ -179,20 +189,20 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
         const float2 y = (i & 1) ? cascade(k, s, u, sg[i], eo) : cascade(k, s, u, sg[i], ee);
         float e = 0.f;
         if (ENV > 0) e = envelope<ENV>(p, s, y);
-        if (OUT) {
+        if (OUT == 2) {
             if (o.gfb) {
-                if (active) __stcs(o.gfb, y.x);
+                if (active) __stcs(o.gfb, k.g4 * y.x);
                 o.gfb += o.C;
             }
             if (ENV > 0 && o.env) {
-                if (active) __stcs(o.env, e);
+                if (active) __stcs(o.env, o.env_scale * e);
                 o.env += o.C;
             }
-            if (ENV > 0 && o.dec && o.next_dec == t + i) {
-                if (active) __stcs(o.dec, e);
-                o.dec += o.C;
-                o.next_dec += o.step;
-            }
+        }
+        if (OUT > 0 && ENV > 0 && o.dec && o.next_dec == t + i) {
+            if (active) __stcs(o.dec, o.env_scale * e);
+            o.dec += o.C;
+            o.next_dec += o.step;
         }
     }
 }
@@ -215,15 +225,14 @@ __global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedPara
     Coef k;
     {
         const float* cp = p.chan + (active ? c : 0);
-        const float z = active ? 1.f : 0.f;
-        const float a0 = z * cp[P_A0 * p.c_pad];
-        k.a0 = make_float2(a0, a0);
+        const float on = active ? 1.f : 0.f;
+        k.g4 = on * cp[P_G4 * p.c_pad];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float a1 = z * cp[(P_A1 + i) * p.c_pad];
-            const float cq = z * cp[(P_CQ + i) * p.c_pad];
-            const float ncy = z * cp[(P_NCY + i) * p.c_pad];
-            k.a1[i] = make_float2(a1, a1);
+            const float z = on * cp[(P_Z + i) * p.c_pad];
+            const float cq = on * cp[(P_CQ + i) * p.c_pad];
+            const float ncy = on * cp[(P_NCY + i) * p.c_pad];
+            k.z[i] = make_float2(z, z);
             k.cq[i] = make_float2(cq, cq);
             k.ncy[i] = make_float2(ncy, ncy);
         }
@@ -235,6 +244,7 @@ __global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedPara
     tE0 = tE0 > 0 ? (tE0 / kTile) * kTile : 0;
     const bool need_env = p.env_t != nullptr || p.dec != nullptr;
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
+    const bool full_out = p.gfb_t != nullptr || p.env_t != nullptr;
     const int nE = need_imag ? (n - tE0 + kTile - 1) / kTile : 0;
     const int w_lpf = (p.lpf && need_env) ? p.w_lpf : 0;
     int ts, tenv;
@@ -276,6 +286,7 @@ __global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedPara
     OutCtx o;
     o.C = (size_t)p.C;
     o.step = p.step;
+    o.env_scale = p.lpf ? k.g4 * p.lp_b0 : k.g4;
     o.gfb = p.gfb_t ? p.gfb_t + (size_t)(ut.full_off + t0) * o.C + (active ? c : 0) : nullptr;
     o.env = p.env_t ? p.env_t + (size_t)(ut.full_off + t0) * o.C + (active ? c : 0) : nullptr;
     {
@@ -307,15 +318,16 @@ __global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedPara
             const int cnt = min(kTile, n - t);
             for (int i = 0; i < cnt; ++i) cascade_real(k, s, sxz[i].x);
             if (kk == nE - 1) {
-                // residuals of the zero-padded ring equation at ring positions n, n+1:
-                //   e0 = b1*y[n-1] + b2*y[n-2] - a1k*u[n-1] = (cy-1)*y - cq*q - a1k*u
-                //   e1 = b2*y[n-1] = cq*y              (y, q, u: stage states after sample n-1)
+                // residuals of the zero-padded ring equation at ring positions n, n+1, in the
+                // scaled stage variables (y, q, u: stage states after sample n-1):
+                //   e0 = b1*y[n-1] + b2*y[n-2] - z_k*u[n-1] = (cy-1)*y - cq*q - z_k*u
+                //   e1 = b2*y[n-1] = cq*y
                 float e0[4], e1[4];
                 float uprev = s.up.x;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float cy = -k.ncy[i].x;
-                    e0[i] = fmaf(cy - 1.0f, s.y[i].x, -k.cq[i].x * s.q[i].x) - k.a1[i].x * uprev;
+                    e0[i] = fmaf(cy - 1.0f, s.y[i].x, -k.cq[i].x * s.q[i].x) - k.z[i].x * uprev;
                     e1[i] = k.cq[i].x * s.y[i].x;
                     uprev = s.y[i].x;
                 }
@@ -331,15 +343,18 @@ __global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedPara
         } else {
             const int cnt = min(kTile, t1 - t);
             if (t < 0) {
-                run_tile<0, false, true>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<0, 0, true>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (t < tenv) {
-                run_tile<0, false, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<0, 0, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (t < t0) {
-                run_tile<2, false, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-            } else if (p.lpf) {
-                run_tile<2, true, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<2, 0, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+            } else if (full_out) {
+                if (p.lpf) run_tile<2, 2, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else if (need_env) run_tile<1, 2, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<0, 2, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else {
-                run_tile<1, true, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                if (p.lpf) run_tile<2, 1, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<1, 1, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             }
         }
         __syncthreads();  // every warp is done with buffer b

@@ -92,6 +92,29 @@ cudaError_t launch_gather_index(const float* src, const long long* idx, long lon
     return cudaGetLastError();
 }
 
+// out[(w*dots + j)*C + c] = (float) env[c*n + idx[w*dots + j]]: the gather of
+// InputGenerator.py:73-80 from a (C,n) matrix in the reference's own layout (loaded .ENV1.npy);
+// the float64 -> float32 conversion rounds to nearest even like numpy.astype (:83).
+template <typename T>
+__global__ void gather_cn_kernel(const T* __restrict__ env, int C, long long n, const long long* __restrict__ idx,
+                                 float* __restrict__ out) {
+    const long long r = blockIdx.x;
+    const long long t = idx[r];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)r * C + c] = (float)env[(size_t)c * n + t];
+}
+
+cudaError_t launch_gather_cn(const void* env, int dtype, int C, long long n, const long long* idx, long long n_idx,
+                             float* out, cudaStream_t stream) {
+    if (n_idx <= 0) return cudaSuccess;
+    if (dtype == F2_DT_F64)
+        gather_cn_kernel<double><<<(unsigned)n_idx, 128, 0, stream>>>((const double*)env, C, n, idx, out);
+    else if (dtype == F2_DT_F32)
+        gather_cn_kernel<float><<<(unsigned)n_idx, 128, 0, stream>>>((const float*)env, C, n, idx, out);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // Dense framing: frame i (i0 <= i < i1) = rows env_t[i + k*step], k < dots.  With
 // `normalize`, Training.normalizeInput per frame: (log v - log min)/(log max - log min),
@@ -165,8 +188,10 @@ cudaError_t launch_dense_frames(const float* env_t, int C, int dots, int step, l
 // folded in, and each lane then corrects its 8 outputs with k^(j+1) * (state at chunk start).
 constexpr int kScanPerLane = 8;
 
+// op: 0 = envelope |x + i xi|, 1 = xi alone (imaginary part of paddedHilbert), 2 = x alone
+// (lowPassFilter of the raw rows).
 template <typename T>
-__global__ void rows_envelope_kernel(const UttDesc* rows, const float2* __restrict__ xz, int lpf, float lp_k,
+__global__ void rows_envelope_kernel(const UttDesc* rows, const float2* __restrict__ xz, int op, int lpf, float lp_k,
                                      float lp_b0, T* __restrict__ out) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -188,7 +213,7 @@ __global__ void rows_envelope_kernel(const UttDesc* rows, const float2* __restri
             const int t = t0 + j;
             float2 v = make_float2(0.f, 0.f);
             if (t < n) v = src[t];
-            e[j] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
+            e[j] = op == 0 ? sqrtf(fmaf(v.x, v.x, v.y * v.y)) : (op == 1 ? v.y : v.x);
         }
         if (!lpf) {
 #pragma unroll
@@ -230,15 +255,15 @@ __global__ void rows_envelope_kernel(const UttDesc* rows, const float2* __restri
     }
 }
 
-cudaError_t launch_rows_envelope(const UttDesc* rows, int n_rows, const float2* xz, int lpf, float lp_k,
+cudaError_t launch_rows_envelope(const UttDesc* rows, int n_rows, const float2* xz, int op, int lpf, float lp_k,
                                  float lp_b0, void* out, int out_dtype, cudaStream_t stream) {
     if (n_rows <= 0) return cudaSuccess;
     // one warp per row, 4 warps per CTA; n_rows is padded by the caller to a multiple of 4
     const int blocks = (n_rows + 3) / 4;
     if (out_dtype == F2_DT_F64)
-        rows_envelope_kernel<double><<<blocks, 128, 0, stream>>>(rows, xz, lpf, lp_k, lp_b0, (double*)out);
+        rows_envelope_kernel<double><<<blocks, 128, 0, stream>>>(rows, xz, op, lpf, lp_k, lp_b0, (double*)out);
     else if (out_dtype == F2_DT_F32)
-        rows_envelope_kernel<float><<<blocks, 128, 0, stream>>>(rows, xz, lpf, lp_k, lp_b0, (float*)out);
+        rows_envelope_kernel<float><<<blocks, 128, 0, stream>>>(rows, xz, op, lpf, lp_k, lp_b0, (float*)out);
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();

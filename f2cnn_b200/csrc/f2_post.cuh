@@ -13,7 +13,9 @@ cudaError_t launch_gather_index(const float* src, const long long* idx, long lon
                                 cudaStream_t stream);
 cudaError_t launch_dense_frames(const float* env_t, int C, int dots, int step, long long i0, long long i1,
                                 int normalize, void* out, int out_dtype, int* bad_flag, cudaStream_t stream);
-cudaError_t launch_rows_envelope(const UttDesc* rows, int n_rows, const float2* xz, int lpf, float lp_k,
+cudaError_t launch_gather_cn(const void* env, int dtype, int C, long long n, const long long* idx, long long n_idx,
+                             float* out, cudaStream_t stream);
+cudaError_t launch_rows_envelope(const UttDesc* rows, int n_rows, const float2* xz, int op, int lpf, float lp_k,
                                  float lp_b0, void* out, int out_dtype, cudaStream_t stream);
 
 }  // namespace f2

@@ -1,0 +1,82 @@
+"""Make the reference's own code run on this package.
+
+    import f2cnn_b200.dropin as dropin
+    dropin.install()            # before `import f2cnn` / `from scripts... import ...`
+
+install() registers this package's drop-in modules in sys.modules under the reference's
+module paths:
+    gammatone, gammatone.filters
+    scripts.processing.GammatoneFiltering / EnvelopeExtraction / InputGenerator
+Everything else under `scripts` (LabelDataGenerator, CNN, plotting, readers ...) keeps
+resolving to the reference tree, which must be importable (on sys.path) if those are used.
+Modules of the reference that were imported BEFORE install() and bound hot-path functions by
+name (`from ... import GetFilteredOutputFromArray`, Evaluating.py:19-21,
+PlottingProcessing.py:13-15) are re-bound in place.
+"""
+import importlib
+import sys
+
+_MODULES = {
+    "gammatone": "f2cnn_b200.gammatone",
+    "gammatone.filters": "f2cnn_b200.gammatone.filters",
+    "scripts.processing.GammatoneFiltering": "f2cnn_b200.scripts.processing.GammatoneFiltering",
+    "scripts.processing.EnvelopeExtraction": "f2cnn_b200.scripts.processing.EnvelopeExtraction",
+    "scripts.processing.InputGenerator": "f2cnn_b200.scripts.processing.InputGenerator",
+}
+
+# names that reference modules bind with `from X import name`
+_REBIND = {
+    "scripts.CNN.Evaluating": {
+        "ExtractEnvelopeFromMatrix": ("scripts.processing.EnvelopeExtraction", "ExtractEnvelopeFromMatrix"),
+        "GetArrayFromWAV": ("scripts.processing.GammatoneFiltering", "GetArrayFromWAV"),
+        "GetFilteredOutputFromArray": ("scripts.processing.GammatoneFiltering", "GetFilteredOutputFromArray"),
+        "filters": ("gammatone", "filters"),
+    },
+    "scripts.plotting.PlottingProcessing": {
+        "ExtractEnvelopeFromMatrix": ("scripts.processing.EnvelopeExtraction", "ExtractEnvelopeFromMatrix"),
+        "GetArrayFromWAV": ("scripts.processing.GammatoneFiltering", "GetArrayFromWAV"),
+        "GetFilteredOutputFromArray": ("scripts.processing.GammatoneFiltering", "GetFilteredOutputFromArray"),
+        "filters": ("gammatone", "filters"),
+    },
+    "scripts.processing.LabelDataGenerator": {
+        "GetArrayFromWAV": ("scripts.processing.GammatoneFiltering", "GetArrayFromWAV"),
+    },
+    "f2cnn": {
+        "FilterAllOrganisedFiles": ("scripts.processing.GammatoneFiltering", "FilterAllOrganisedFiles"),
+        "ExtractAllEnvelopes": ("scripts.processing.EnvelopeExtraction", "ExtractAllEnvelopes"),
+        "GenerateInputData": ("scripts.processing.InputGenerator", "GenerateInputData"),
+    },
+}
+
+_installed = {}
+
+
+def install():
+    """Idempotent.  Returns the dict {reference module path: drop-in module}."""
+    for ref_name, ours in _MODULES.items():
+        mod = importlib.import_module(ours)
+        prev = sys.modules.get(ref_name)
+        if prev is not None and prev is not mod:
+            _installed.setdefault(ref_name, prev)
+        sys.modules[ref_name] = mod
+        parent, _, leaf = ref_name.rpartition(".")
+        if parent and parent in sys.modules:
+            setattr(sys.modules[parent], leaf, mod)
+    for importer, names in _REBIND.items():
+        m = sys.modules.get(importer)
+        if m is None:
+            continue
+        for attr, (src, name) in names.items():
+            if hasattr(m, attr):
+                setattr(m, attr, getattr(sys.modules[src], name))
+    return {k: sys.modules[k] for k in _MODULES}
+
+
+def uninstall():
+    """Restore whatever install() displaced (used by tests)."""
+    for ref_name in _MODULES:
+        prev = _installed.pop(ref_name, None)
+        if prev is not None:
+            sys.modules[ref_name] = prev
+        elif sys.modules.get(ref_name) is not None and sys.modules[ref_name].__name__.startswith("f2cnn_b200"):
+            del sys.modules[ref_name]

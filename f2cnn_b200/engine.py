@@ -83,16 +83,15 @@ class Plan:
         return self._ws
 
     # -- stand-alone envelope of matrix rows (ExtractEnvelopeFromMatrix on foreign data) ----
-    def envelope_rows(self, matrix_dev, lpf, cutoff, out_dtype=torch.float64, stream=None):
+    def envelope_rows(self, matrix_dev, lpf, cutoff, out_dtype=torch.float64, stream=None, op=0):
         rows, n = matrix_dev.shape
         out = torch.empty((rows, n), dtype=out_dtype, device=self.device)
         if rows == 0 or n == 0:
             return out
         L = _native.lib()
         ws = self.workspace(L.f2_envelope_rows_workspace_bytes(rows, n))
-        check(L.f2_envelope_rows(self._h, _ptr(matrix_dev), _T2F2[matrix_dev.dtype], rows, n, int(bool(lpf)),
-                                 float(cutoff), _ptr(out), _T2F2[out_dtype], _ptr(ws), ws.numel(),
-                                 _stream_ptr(stream)))
+        check(L.f2_rows_op(self._h, _ptr(matrix_dev), _T2F2[matrix_dev.dtype], rows, n, int(op), int(bool(lpf)),
+                           float(cutoff), _ptr(out), _T2F2[out_dtype], _ptr(ws), ws.numel(), _stream_ptr(stream)))
         return out
 
 
@@ -212,6 +211,17 @@ def gather_index(src_dev, idx_dev, out=None, stream=None):
     if out is None:
         out = torch.empty((n, C), dtype=torch.float32, device=src_dev.device)
     check(_native.lib().f2_gather_index(_ptr(src_dev), C, _ptr(idx_dev), n, _ptr(out), _stream_ptr(stream)))
+    return out
+
+
+def gather_windows_cn(env_dev, idx_dev, out=None, stream=None):
+    """out[i, :] = float32(env[:, idx[i]]) for a (C, n) float64/float32 device matrix."""
+    C, n = int(env_dev.shape[0]), int(env_dev.shape[1])
+    m = int(idx_dev.numel())
+    if out is None:
+        out = torch.empty((m, C), dtype=torch.float32, device=env_dev.device)
+    check(_native.lib().f2_gather_windows_cn(_ptr(env_dev), _T2F2[env_dev.dtype], C, n, _ptr(idx_dev), m, _ptr(out),
+                                             _stream_ptr(stream)))
     return out
 
 

@@ -109,6 +109,16 @@ F2_API int f2_envelope_rows(f2_plan* plan, const void* matrix, int dtype, int64_
                      double cutoff_hz, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* The same machinery for the two other row-wise functions of EnvelopeExtraction.py:
+ * F2_ROWS_HILBERT = imaginary part of paddedHilbert(row) (:20-36), F2_ROWS_LOWPASS =
+ * lowPassFilter(row, cutoff) alone (:39-48, lpf must be 1).  F2_ROWS_ENVELOPE == f2_envelope_rows. */
+#define F2_ROWS_ENVELOPE 0
+#define F2_ROWS_HILBERT 1
+#define F2_ROWS_LOWPASS 2
+F2_API int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64_t n, int op, int lpf,
+                      double cutoff_hz, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ---- windowing ---------------------------------------------------------------------------
  * out[w][j][c] = frames[base_rows[w] + j*stride_rows][c], j < dots: the window gather of
  * InputGenerator.py:73-80 on decimated frames (base = frame of center - RADIUS*STEP,
@@ -117,6 +127,10 @@ F2_API int f2_gather_windows(const float* frames, int n_channels, const int64_t*
                       int64_t stride_rows, float* out, void* stream);
 /* out[i][c] = src[idx[i]][c]: arbitrary rows (timepoints that wrap like a negative Python index). */
 F2_API int f2_gather_index(const float* src, int n_channels, const int64_t* idx, int64_t n_idx, float* out, void* stream);
+/* out[i][c] = (float) env[c*n + idx[i]]: the same gather from a (C,n) matrix in the reference's
+ * own layout (a loaded .ENV1.npy, InputGenerator.py:72); F2_F64 -> float32 rounds like numpy. */
+F2_API int f2_gather_windows_cn(const void* env, int dtype, int n_channels, int64_t n, const int64_t* idx,
+                                int64_t n_idx, float* out, void* stream);
 /* Dense framing of Evaluating.py:70-78: frame i = env_t rows i + k*step, k < dots, for
  * i0 <= i < i1; normalize != 0 applies Training.normalizeInput (Training.py:13-28) per frame
  * and sets *bad_flag (device int) when a frame has a value <= 0 (the reference raises). */

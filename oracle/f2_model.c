@@ -9,9 +9,9 @@
  *
  * Per channel (parameters prepared in float64, rounded once to float32):
  *   cq = B2, cy = 1 + B1 + B2   (pole pair, "delta" form: q = y[t]-y[t-1])
- *   a0 = A0/g^(1/4), a1[k] = A1k/g^(1/4)   (gain folded per stage)
+ *   z[k] = A1k/A0 (stage zero), g4 = A0^4/gain (output scale; stages run without a0)
  * Stage update (input u[t], up = u[t-1]):
- *   in = a0*u + a1*up (+ e*G[t] on the imaginary path)
+ *   in = u + z*up (+ e*G[t] on the imaginary path)
  *   q  = cq*q + in ; q = q - cy*y ; y = y + q
  */
 #include <math.h>
@@ -20,7 +20,7 @@
 #include <string.h>
 
 typedef struct {
-    float cq[4], cy[4], a0, a1[4], s[4]; /* s[k] = a0 + a1[k] (form 1) */
+    float cq[4], cy[4], z[4], g4;
 } chan_t;
 
 /* Round c to float32 per stage so that the four stage values sum to 4*c as closely as
@@ -41,27 +41,19 @@ static void dither4(double c, float *out)
 
 static void prep(const double *k10, chan_t *p)
 {
-    double gq = pow(k10[9], 0.25);
-    double a0 = k10[0] / gq;
     dither4(k10[8], p->cq);
     dither4(1.0 + k10[7] + k10[8], p->cy);
-    p->a0 = (float)a0;
-    for (int k = 0; k < 4; ++k) {
-        p->a1[k] = (float)(k10[1 + k] / gq);
-        p->s[k] = (float)((k10[0] + k10[1 + k]) / gq);
-    }
+    p->g4 = (float)(k10[0] * k10[0] * k10[0] * k10[0] / k10[9]);
+    for (int k = 0; k < 4; ++k) p->z[k] = (float)(k10[1 + k] / k10[0]);
 }
 
 /* one cascade step on one path.  y[4], q[4] states; u = input sample, up = previous
- * input; inj[k] = injection for stage k (0 on the real path).  form 0: in = a0*u+a1*up;
- * form 1: in = a0*(u-up) + s*up with stage>=2 using q of the previous stage. */
+ * input; inj[k] = injection for stage k (0 on the real path). */
 static inline float cascade_step(const chan_t *p, float *y, float *q, float u, float up, const float *inj, int form)
 {
-    float du = u - up;
+    (void)form;
     for (int k = 0; k < 4; ++k) {
-        float in;
-        if (form == 0) in = fmaf(p->a0, u, p->a1[k] * up);
-        else in = fmaf(p->a0, du, p->s[k] * up);
+        float in = fmaf(p->z[k], up, u);
         if (inj) in = in + inj[k];
         float yold = y[k];
         float qn = fmaf(p->cq[k], q[k], in);
@@ -71,7 +63,6 @@ static inline float cascade_step(const chan_t *p, float *y, float *q, float u, f
         y[k] = yn;
         up = yold; /* next stage: previous input = this stage's previous output */
         u = yn;
-        du = qn;
     }
     return y[3];
 }
@@ -98,7 +89,7 @@ void f2m_run(const float *xf, const float *xi, const float *G, int64_t n, int64_
         float e0[4], e1[4];
         for (int k = 0; k < 4; ++k) {
             float uprev = (k == 0) ? (n > 0 ? xf[n - 1] : 0.0f) : y[k - 1];
-            e0[k] = fmaf(p.cy[k] - 1.0f, y[k], -p.cq[k] * q[k]) - p.a1[k] * uprev;
+            e0[k] = fmaf(p.cy[k] - 1.0f, y[k], -p.cq[k] * q[k]) - p.z[k] * uprev;
             e1[k] = p.cq[k] * y[k];
         }
         /* imaginary path: periodic steady state by a W-sample warm-up on the ring */
@@ -130,15 +121,15 @@ void f2m_run(const float *xf, const float *xi, const float *G, int64_t n, int64_
                 yi = cascade_step(&p, vy, vq, xi[t], vup, inj, form);
                 vup = xi[t];
             }
-            if (out_gfb) out_gfb[(size_t)c * n + t] = yr;
+            if (out_gfb) out_gfb[(size_t)c * n + t] = p.g4 * yr;
             if (out_env) {
                 float e = sqrtf(fmaf(yr, yr, yi * yi));
                 if (lpf) {
                     /* l~ = (e + eprev) + k*l~ ; out = b0*l~ */
                     l = fmaf(k_lp, l, e + eprev);
                     eprev = e;
-                    out_env[(size_t)c * n + t] = b0_lp * l;
-                } else out_env[(size_t)c * n + t] = e;
+                    out_env[(size_t)c * n + t] = (p.g4 * b0_lp) * l;
+                } else out_env[(size_t)c * n + t] = p.g4 * e;
             }
         }
     }
