@@ -39,6 +39,8 @@
 // imaginary path (w_imag samples before t=0 on the ring).
 #include "f2_fused.cuh"
 
+#include <stdlib.h>
+
 namespace f2 {
 
 struct Coef {
@@ -132,16 +134,16 @@ __device__ __forceinline__ float envelope(const FusedParams& p, State& s, float2
     return e;
 }
 
-template <int ENV, int OUT, bool ZEROX>
+template <int ENV, int OUT, bool ZEROX, int U>
 __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, State& s, const float (&ee)[4],
                                          const float (&eo)[4], const float2* __restrict__ sxz,
                                          const float* __restrict__ sg, int t, int cnt, bool active, OutCtx& o) {
     int i = 0;
-    for (; i + 8 <= cnt; i += 8) {
-        float xv[16];
-        float gv[8];
+    for (; i + U <= cnt; i += U) {
+        float xv[2 * U];
+        float gv[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < U / 2; ++j) {
             const float4 v = *reinterpret_cast<const float4*>(sxz + i + 2 * j);
             xv[4 * j + 0] = v.x;
             xv[4 * j + 1] = v.y;
@@ -149,16 +151,16 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             xv[4 * j + 3] = v.w;
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < U / 4; ++j) {
             const float4 v = *reinterpret_cast<const float4*>(sg + i + 4 * j);
             gv[4 * j + 0] = v.x;
             gv[4 * j + 1] = v.y;
             gv[4 * j + 2] = v.z;
             gv[4 * j + 3] = v.w;
         }
-        float ev[8];
+        float ev[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < U; ++j) {
             const float2 u = make_float2(ZEROX ? 0.f : xv[2 * j], xv[2 * j + 1]);
             const float2 y = (j & 1) ? cascade(k, s, u, gv[j], eo) : cascade(k, s, u, gv[j], ee);
             if (ENV > 0) ev[j] = envelope<ENV>(p, s, y);
@@ -168,15 +170,15 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             }
         }
         if (OUT == 2) {
-            if (o.gfb) o.gfb += 8 * o.C;
-            if (o.env) o.env += 8 * o.C;
+            if (o.gfb) o.gfb += U * o.C;
+            if (o.env) o.env += U * o.C;
         }
         if (OUT > 0 && ENV > 0 && o.dec) {
-            while (o.next_dec < t + i + 8) {
+            while (o.next_dec < t + i + U) {
                 const int r = o.next_dec - (t + i);
                 float v = ev[0];
 #pragma unroll
-                for (int j = 1; j < 8; ++j) v = (r == j) ? ev[j] : v;
+                for (int j = 1; j < U; ++j) v = (r == j) ? ev[j] : v;
                 if (active) __stcs(o.dec, o.env_scale * v);
                 o.dec += o.C;
                 o.next_dec += o.step;
@@ -207,7 +209,8 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
     }
 }
 
-__global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedParams p) {
+template <int MINB, int U>
+__global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedParams p) {
     __shared__ __align__(128) float2 s_xz[kStages][kTile];
     __shared__ __align__(128) float s_g[kStages][kTile];
     __shared__ __align__(8) uint64_t s_full[kStages];
@@ -343,18 +346,18 @@ __global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedPara
         } else {
             const int cnt = min(kTile, t1 - t);
             if (t < 0) {
-                run_tile<0, 0, true>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<0, 0, true, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (t < tenv) {
-                run_tile<0, 0, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<0, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (t < t0) {
-                run_tile<2, 0, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<2, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (full_out) {
-                if (p.lpf) run_tile<2, 2, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else if (need_env) run_tile<1, 2, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else run_tile<0, 2, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                if (p.lpf) run_tile<2, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else if (need_env) run_tile<1, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<0, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else {
-                if (p.lpf) run_tile<2, 1, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else run_tile<1, 1, false>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                if (p.lpf) run_tile<2, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<1, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             }
         }
         __syncthreads();  // every warp is done with buffer b
@@ -364,7 +367,22 @@ __global__ void __launch_bounds__(kChanPerBlock, 4) fused_kernel(const FusedPara
 
 cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream) {
     if (n_items <= 0) return cudaSuccess;
-    fused_kernel<<<n_items, kChanPerBlock, 0, stream>>>(p);
+    // tuning knob (development only): F2_FUSED_VARIANT = "<min blocks per SM><unroll>"
+    static int variant = -1;
+    if (variant < 0) {
+        const char* v = getenv("F2_FUSED_VARIANT");
+        variant = v ? atoi(v) : 0;
+    }
+    switch (variant) {
+        case 58: fused_kernel<5, 8><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 68: fused_kernel<6, 8><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 44: fused_kernel<4, 4><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 54: fused_kernel<5, 4><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 64: fused_kernel<6, 4><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 416: fused_kernel<4, 16><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 316: fused_kernel<3, 16><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        default: fused_kernel<4, 8><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+    }
     return cudaGetLastError();
 }
 

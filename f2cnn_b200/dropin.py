@@ -51,8 +51,27 @@ _REBIND = {
 _installed = {}
 
 
+def _ensure_parent_packages():
+    """`scripts` and `scripts.processing` come from the reference tree when it is importable
+    (so that LabelDataGenerator, CNN, plotting ... keep resolving); otherwise this package's
+    own `scripts` packages stand in, so that the hot-path modules import on their own."""
+    for ref_pkg, ours in (("scripts", "f2cnn_b200.scripts"), ("scripts.processing", "f2cnn_b200.scripts.processing")):
+        if ref_pkg in sys.modules:
+            continue
+        try:
+            importlib.import_module(ref_pkg)
+        except ImportError:
+            mod = importlib.import_module(ours)
+            sys.modules[ref_pkg] = mod
+            _installed.setdefault(ref_pkg, None)
+            parent, _, leaf = ref_pkg.rpartition(".")
+            if parent and parent in sys.modules:
+                setattr(sys.modules[parent], leaf, mod)
+
+
 def install():
     """Idempotent.  Returns the dict {reference module path: drop-in module}."""
+    _ensure_parent_packages()
     for ref_name, ours in _MODULES.items():
         mod = importlib.import_module(ours)
         prev = sys.modules.get(ref_name)
@@ -74,7 +93,7 @@ def install():
 
 def uninstall():
     """Restore whatever install() displaced (used by tests)."""
-    for ref_name in _MODULES:
+    for ref_name in list(_MODULES) + ["scripts.processing", "scripts"]:
         prev = _installed.pop(ref_name, None)
         if prev is not None:
             sys.modules[ref_name] = prev

@@ -16,7 +16,7 @@ from multiprocessing import Value
 
 import numpy
 
-from ..gammatone import filters
+from ...gammatone import filters
 
 counter = None
 FILTERBANK_COEFFICIENTS = None

@@ -1,0 +1,142 @@
+"""CPU-only checks (-m "not gpu"): coefficient design is bit-identical to the reference, the
+C-ABI library loads and exports every symbol include/f2cnn_b200.h declares, host-side index
+logic matches the reference's Python semantics, and the product refuses to run without CUDA
+instead of falling back."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_filters_bit_exact_vs_reference_golden():
+    from f2cnn_b200.gammatone import filters
+    g = load_golden("coefs.npz")
+    for tag, (fs, C, low) in {"fs16000_c128_l100": (16000, 128, 100), "fs16000_c256_l100": (16000, 256, 100),
+                              "fs16000_c8_l100": (16000, 8, 100), "fs8000_c32_l50": (8000, 32, 50),
+                              "fs44100_c64_l20": (44100, 64, 20)}.items():
+        cf = filters.centre_freqs(fs, C, low)
+        assert np.array_equal(cf, g["cf_" + tag])
+        assert np.array_equal(filters.make_erb_filters(fs, cf), g["coefs_" + tag])
+    assert np.array_equal(filters.erb_space(), g["erb_space_default"])
+    assert np.array_equal(filters.make_erb_filters(16000, filters.centre_freqs(16000, 16, 100), width=2.0),
+                          g["coefs_width2"])
+    assert filters.DEFAULT_FILTER_NUM == 100 and filters.DEFAULT_LOW_FREQ == 100
+    assert filters.DEFAULT_HIGH_FREQ == 44100 / 4
+    assert filters.erb_point(100, 8000, 1) == pytest.approx(100.0)
+    assert filters.erb_point(100, 8000, 0) == pytest.approx(8000.0)
+
+
+def test_library_exports_every_declared_symbol():
+    from f2cnn_b200 import _native
+    header = open(os.path.join(ROOT, "include", "f2cnn_b200.h")).read()
+    declared = set(re.findall(r"F2_API\s+[\w\s\*]+?\b(f2_\w+)\s*\(", header))
+    assert len(declared) >= 25
+    L = _native.lib()  # raises if the .so is missing or a bound symbol is absent
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert L.f2_abi_version() == _native.ABI_VERSION
+
+
+def test_lowpass_coefficients_match_scipy_butter_golden():
+    from f2cnn_b200 import engine
+    g = load_golden("coefs.npz")
+    for f in (20, 50, 100, 400):
+        b0, a1 = engine.lowpass_coefficients(f)
+        np.testing.assert_allclose([b0, b0, 1.0, a1], g["butter_%d" % f], rtol=1e-13)
+    from f2cnn_b200._native import F2Error
+    with pytest.raises(F2Error):
+        engine.lowpass_coefficients(9000)
+
+
+def test_window_indices_python_list_semantics():
+    from f2cnn_b200 import api
+    idx = api.window_indices(2000, [800, 100], 5, 160)
+    assert idx.shape == (2, 11)
+    assert list(idx[0]) == [160 * k for k in range(11)]
+    assert idx[1, 0] == 2000 - 700 and idx[1, 5] == 100  # negative index wraps once, like env[ch][-700]
+    with pytest.raises(IndexError):
+        api.window_indices(2000, [1300], 5, 160)
+    with pytest.raises(IndexError):
+        api.window_indices(500, [100], 5, 160)  # -700 + 500 still negative
+
+
+def test_label_grid_matches_reference_formula():
+    from f2cnn_b200 import synth
+    g = synth.label_grid(48000)
+    assert len(g) == int(48000 / 160 - 11 - 1) == 288 and g[0] == 800 and g[-1] == 800 + 287 * 160
+    assert len(synth.label_grid(1000)) == 0
+
+
+def test_csv_parsing_and_row_order(tmp_path):
+    from f2cnn_b200.scripts.processing import InputGenerator
+    p = tmp_path / "labels.csv"
+    p.write_text("TRAIN,DR2,S1,SX1,aa,960,0.1,0.01,1\nTEST,DR1,S0,SA1,iy,800,0.2,0.02,0\n"
+                 "TRAIN,DR2,S1,SX1,aa,800,0.1,0.01,1\n")
+    d = InputGenerator.GetListOfEnvelopeFilesAndTimepoints(str(p))
+    assert list(d) == [os.path.join("TRAIN", "DR2.S1.SX1.ENV1.npy"), os.path.join("TEST", "DR1.S0.SA1.ENV1.npy")]
+    assert d[os.path.join("TRAIN", "DR2.S1.SX1.ENV1.npy")] == [960, 800]  # CSV order kept within a file
+
+
+def test_nist_sphere_and_riff_readers(tmp_path):
+    from scipy.io import wavfile
+    from f2cnn_b200.scripts.processing import GammatoneFiltering as GF
+    x = (np.arange(1000) * 7 % 2000 - 1000).astype(np.int16)
+    riff = tmp_path / "a.WAV"
+    wavfile.write(str(riff), 16000, x)
+    fs, y = GF.GetArrayFromWAV(str(riff))
+    assert fs == 16000 and np.array_equal(x, y)
+    hdr = ("NIST_1A\n   1024\nsample_count -i %d\nsample_rate -i 16000\nchannel_count -i 1\n"
+           "sample_n_bytes -i 2\nsample_byte_format -s2 01\nsample_coding -s3 pcm\nend_head\n" % len(x)).encode()
+    sph = tmp_path / "b.WAV"
+    sph.write_bytes(hdr + b" " * (1024 - len(hdr)) + x.astype("<i2").tobytes())
+    fs, y = GF.GetArrayFromWAV(str(sph))
+    assert fs == 16000 and y.dtype == np.int16 and np.array_equal(x, y)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from f2cnn_b200 import api
+    from f2cnn_b200.gammatone import filters
+    co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 8, 100))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        api.erb_filterbank(np.zeros(100, dtype=np.int16), co)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        filters.erb_filterbank(np.zeros(100, dtype=np.int16), co)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under f2cnn_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "f2cnn_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("float64 oracle", "").replace("same oracle", ""), os.path.join(dirpath, f)
+
+
+def test_dropin_install_registers_reference_module_paths():
+    from f2cnn_b200 import dropin
+    mods = dropin.install()
+    try:
+        import gammatone.filters as gf
+        from scripts.processing import EnvelopeExtraction, GammatoneFiltering, InputGenerator
+        assert gf.__name__ == "f2cnn_b200.gammatone.filters"
+        assert GammatoneFiltering.__name__.startswith("f2cnn_b200.")
+        for name in ("GetArrayFromWAV", "GetFilteredOutputFromArray", "GetFilteredOutputFromFile", "saveGFBMatrix",
+                     "loadGFBMatrix", "GammatoneFiltering", "InitProcesses", "FilterAllOrganisedFiles"):
+            assert callable(getattr(GammatoneFiltering, name))
+        for name in ("paddedHilbert", "lowPassFilter", "ExtractEnvelopeFromMatrix", "ExtractEnvelope", "SaveEnvelope",
+                     "ExtractAndSaveEnvelope", "InitProcesses", "ExtractAllEnvelopes"):
+            assert callable(getattr(EnvelopeExtraction, name))
+        for name in ("GetListOfEnvelopeFilesAndTimepoints", "GenerateInputData"):
+            assert callable(getattr(InputGenerator, name))
+        assert len(mods) == 5
+    finally:
+        dropin.uninstall()
