@@ -381,7 +381,8 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     pp.utts = b->d_utts;
     pp.wave = a->wave;
     pp.wave_dtype = a->wave_dtype;
-    pp.Z = Z;
+    pp.bufA = G;   // the table ends up where the forward transform's first scratch was
+    pp.bufB = Z;
     pp.xz = xz;
     pp.G = G;
     pp.hilbert = need_env ? 1 : 0;
@@ -460,7 +461,7 @@ __global__ void rows_desc_kernel(f2::UttDesc* d, long long rows, long long rows_
 size_t f2_envelope_rows_workspace_bytes(int64_t rows, int64_t n) {
     if (rows <= 0 || n <= 0) return 256;
     const RowLayout r = row_layout(rows, n);
-    return align_up((size_t)r.rows_pad * sizeof(f2::UttDesc), 256) + 3 * ws_ring_bytes(r.ring_len * rows) + 256;
+    return align_up((size_t)r.rows_pad * sizeof(f2::UttDesc), 256) + 4 * ws_ring_bytes(r.ring_len * rows) + 256;
 }
 
 int f2_envelope_rows(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64_t n, int lpf,
@@ -498,6 +499,7 @@ int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64
     const size_t rb = ws_ring_bytes(r.ring_len * rows);
     float* Z = (float*)ws;
     float2* xz = (float2*)(ws + rb);
+    float* Z2 = (float*)(ws + 3 * rb);
     rows_desc_kernel<<<(unsigned)((r.rows_pad + 127) / 128), 128, 0, stream>>>(d_rows, rows, r.rows_pad, (int)n, r.lg,
                                                                               r.ring_len);
     F2_CUDA(cudaGetLastError());
@@ -505,7 +507,8 @@ int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64
     pp.utts = d_rows;
     pp.wave = matrix;
     pp.wave_dtype = dtype;
-    pp.Z = Z;
+    pp.bufA = Z;
+    pp.bufB = Z2;
     pp.xz = xz;
     pp.G = nullptr;
     pp.hilbert = op == F2_ROWS_LOWPASS ? 0 : 1;

@@ -6,9 +6,15 @@
 // The ring formulation used by the fused kernel needs only ONE Hilbert transform per
 // utterance, of the zero-padded INPUT: xi = Im(hilbert(pad(x, N2))), N2 = 2^ceil(log2 n).
 // It is computed here with a hand-written FP32 FFT (no cuFFT):
-//   real N2-point FFT as a packed complex M = N2/2 point FFT, split radix-2 in shared
-//   memory, M <= 4096 in one pass, larger M as a four-step (columns, twiddle, rows) FFT
-//   with <= 4096-point legs; untangle, multiply by -i*sgn(k), tangle; inverse FFT.
+//   real N2-point FFT as a packed complex M = N2/2 point FFT; M <= 4096 in one pass, larger
+//   M as a four-step (columns, twiddle, rows) FFT with <= 4096-point shared-memory legs
+//   (radix-4 steps); untangle, multiply by -i*sgn(k), tangle; inverse FFT.
+// Launch sequence (A, B = N2 floats per utterance, XZ = N2 float2):
+//   fft_cols<fwd>  wave -> A      (int16/f32/f64 -> packed complex fused into the load)
+//   fft_rows<fwd>  A    -> B      (single-pass sizes: wave -> B)
+//   hilbert_mask   B in place; also tabulates the injection kernel G into A
+//   fft_cols<inv>  B in place
+//   fft_rows<inv>  B    -> XZ     ((x, xi) interleaved ring, x re-read from the wave)
 // The same kernels serve the stand-alone envelope path (rows of an arbitrary matrix).
 #include "f2_prep.cuh"
 
@@ -39,41 +45,78 @@ cudaError_t init_twiddles(cudaStream_t stream) {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-template <typename T>
-__device__ __forceinline__ float load_sample(const void* base, long long idx) {
-    return (float)reinterpret_cast<const T*>(base)[idx];
-}
-
-__device__ __forceinline__ float load_wave(const void* base, int dtype, long long idx) {
-    switch (dtype) {
-        case F2_DT_I16: return load_sample<short>(base, idx);
-        case F2_DT_F32: return load_sample<float>(base, idx);
-        default: return load_sample<double>(base, idx);
+// packed sample pair (x[2m], x[2m+1]) of an utterance, zero beyond n
+__device__ __forceinline__ float2 load_pair(const void* base, int dtype, long long off, int m, int n) {
+    const int t = 2 * m;
+    float a = 0.f, b = 0.f;
+    if (t < n) {
+        const bool two = t + 1 < n;
+        switch (dtype) {
+            case F2_DT_I16: {
+                const short* p = reinterpret_cast<const short*>(base) + off + t;
+                a = (float)p[0];
+                if (two) b = (float)p[1];
+                break;
+            }
+            case F2_DT_F32: {
+                const float* p = reinterpret_cast<const float*>(base) + off + t;
+                a = p[0];
+                if (two) b = p[1];
+                break;
+            }
+            default: {
+                const double* p = reinterpret_cast<const double*>(base) + off + t;
+                a = (float)p[0];
+                if (two) b = (float)p[1];
+            }
+        }
     }
+    return make_float2(a, b);
 }
 
-// ---- pack: z[m] = (x[2m], x[2m+1]) zero-padded to N2, into Z ------------------------------
-__global__ void pack_kernel(PrepParams p) {
-    const UttDesc ut = p.utts[blockIdx.x];
-    const int M = ut.N2 >> 1;
-    float2* z = reinterpret_cast<float2*>(p.Z + ut.ring_off);
-    for (int m = blockIdx.y * blockDim.x + threadIdx.x; m < M; m += gridDim.y * blockDim.x) {
-        const int t = 2 * m;
-        const float a = t < ut.n ? load_wave(p.wave, p.wave_dtype, ut.wave_off + t) : 0.f;
-        const float b = t + 1 < ut.n ? load_wave(p.wave, p.wave_dtype, ut.wave_off + t + 1) : 0.f;
-        z[m] = make_float2(a, b);
-    }
-}
-
-// ---- in-shared-memory radix-2 DIT FFT on `batch` arrays of length 2^logL ------------------
-// Data already stored bit-reversed.  INV conjugates the twiddles (unnormalised inverse).
+// ---- in-shared-memory DIT FFT on `batch` arrays of length 2^logL (data stored bit-reversed).
+// Two radix-2 stages are fused into one radix-4 step (half the passes and barriers); an odd
+// logL ends with one radix-2 stage.  INV conjugates the twiddles (unnormalised inverse).
 template <bool INV>
 __device__ __forceinline__ void smem_fft(float2* s, int pitch, int logL, int batch) {
-    const int halfL = 1 << (logL - 1);
-    const int total = batch << (logL - 1);
-    for (int st = 0; st < logL; ++st) {
+    int st = 0;
+    for (; st + 2 <= logL; st += 2) {
+        const int h = 1 << st;
+        const int per = 1 << (logL - 2);  // radix-4 butterflies per array
+        const int total = batch << (logL - 2);
+        for (int bf = threadIdx.x; bf < total; bf += blockDim.x) {
+            const int arr = bf >> (logL - 2);
+            const int j = bf & (per - 1);
+            const int pos = j & (h - 1);
+            const int i0 = ((j >> st) << (st + 2)) + pos;
+            float2* a = s + arr * pitch + i0;
+            float2 w1 = g_twiddle[pos << (kTwLog - 1 - st)];  // w_{2h}^pos
+            float2 w2 = g_twiddle[pos << (kTwLog - 2 - st)];  // w_{4h}^pos
+            if (INV) {
+                w1.y = -w1.y;
+                w2.y = -w2.y;
+            }
+            const float2 x0 = a[0], x1 = cmul(a[h], w1), x2 = a[2 * h], x3 = cmul(a[3 * h], w1);
+            const float2 p0 = cadd(x0, x1), p1 = csub(x0, x1);  // stage st: (0,1)
+            const float2 q0 = cadd(x2, x3), q1 = csub(x2, x3);  //           (2,3)
+            // stage st+1: (p0,q0) with w2; (p1,q1) with w2 * w_{4h}^h = w2 * (-i) fwd / (+i) inv
+            const float2 t0 = cmul(q0, w2);
+            const float2 t1r = cmul(q1, w2);
+            const float2 t1 = INV ? make_float2(-t1r.y, t1r.x) : make_float2(t1r.y, -t1r.x);
+            a[0] = cadd(p0, t0);
+            a[2 * h] = csub(p0, t0);
+            a[h] = cadd(p1, t1);
+            a[3 * h] = csub(p1, t1);
+        }
+        __syncthreads();
+    }
+    if (st < logL) {
         const int half = 1 << st;
+        const int halfL = 1 << (logL - 1);
+        const int total = batch << (logL - 1);
         for (int bf = threadIdx.x; bf < total; bf += blockDim.x) {
             const int arr = bf >> (logL - 1);
             const int j = bf & (halfL - 1);
@@ -84,8 +127,8 @@ __device__ __forceinline__ void smem_fft(float2* s, int pitch, int logL, int bat
             if (INV) w.y = -w.y;
             const float2 u = a[i0];
             const float2 v = cmul(a[i0 + half], w);
-            a[i0] = make_float2(u.x + v.x, u.y + v.y);
-            a[i0 + half] = make_float2(u.x - v.x, u.y - v.y);
+            a[i0] = cadd(u, v);
+            a[i0 + half] = csub(u, v);
         }
         __syncthreads();
     }
@@ -104,11 +147,12 @@ __host__ __device__ inline void fft_split(int log2M, int& l1, int& l2) {
 }
 
 // ---- pass A (columns): M1-point FFTs down the columns of the M1 x M2 matrix, then the
-// four-step twiddle w_M^(n2*k1); in place. -------------------------------------------------
-template <bool INV>
-__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(const UttDesc* utts, float* buf_base, int buf_is_xz) {
+// four-step twiddle w_M^(n2*k1).  SRC_WAVE: read the packed input straight from the wave
+// and write to `buf`; otherwise in place on `buf`. ----------------------------------------
+template <bool INV, bool SRC_WAVE>
+__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(PrepParams p, float* buf) {
     extern __shared__ float2 s_fft[];
-    const UttDesc ut = utts[blockIdx.x];
+    const UttDesc ut = p.utts[blockIdx.x];
     const int log2M = ut.log2N2 - 1;
     if (log2M <= kTwLog) return;  // single-pass sizes skip the column pass
     int l1, l2;
@@ -118,12 +162,13 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(const UttDesc* ut
     if (B > M2) B = M2;
     const int c0 = blockIdx.y * B;
     if (c0 >= M2) return;
-    float2* z = reinterpret_cast<float2*>(buf_base + (buf_is_xz ? 2 : 1) * ut.ring_off);
+    float2* z = reinterpret_cast<float2*>(buf + ut.ring_off);
     const int pitch = M1 + 1;
     const int logB = 31 - __clz(B);
     for (int idx = threadIdx.x; idx < (B << l1); idx += blockDim.x) {
         const int n1 = idx >> logB, b = idx & (B - 1);
-        s_fft[b * pitch + bitrev(n1, l1)] = z[(size_t)n1 * M2 + c0 + b];
+        const int e = n1 * M2 + c0 + b;
+        s_fft[b * pitch + bitrev(n1, l1)] = SRC_WAVE ? load_pair(p.wave, p.wave_dtype, ut.wave_off, e, ut.n) : z[e];
     }
     __syncthreads();
     smem_fft<INV>(s_fft, pitch, l1, B);
@@ -138,34 +183,49 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(const UttDesc* ut
     }
 }
 
-// ---- pass B (rows): M2-point FFTs along the rows; output X[k1 + M1*k2] to `out`. ----------
-template <bool INV>
-__global__ void __launch_bounds__(kFftThreads)
-    fft_rows_kernel(const UttDesc* utts, float* in_base, int in_is_xz, float* out_base, int out_is_xz) {
+// ---- pass B (rows): M2-point FFTs along the rows, output index k1 + M1*k2.
+// SRC_WAVE: single-pass forward transform reading the wave.  DST_RING: last pass of the
+// inverse: output m holds (xi[2m], xi[2m+1]); write the interleaved (x, xi) ring directly. ----
+template <bool INV, bool SRC_WAVE, bool DST_RING>
+__global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(PrepParams p, const float* in_buf, float* out_buf) {
     extern __shared__ float2 s_fft[];
-    const UttDesc ut = utts[blockIdx.x];
+    const UttDesc ut = p.utts[blockIdx.x];
     const int log2M = ut.log2N2 - 1;
     if (log2M < 1) return;
     int l1, l2;
     fft_split(log2M, l1, l2);
+    if (SRC_WAVE && l1 != 0) return;   // two-pass sizes were packed by the column pass
+    if (!SRC_WAVE && !INV && l1 == 0) return;  // forward single-pass sizes take the SRC_WAVE launch
     const int M1 = 1 << l1, M2 = 1 << l2;
     int B = kFftSmemPts >> l2;
     if (B > M1) B = M1;
     const int r0 = blockIdx.y * B;
     if (r0 >= M1) return;
-    const float2* zin = reinterpret_cast<const float2*>(in_base + (in_is_xz ? 2 : 1) * ut.ring_off);
-    float2* zout = reinterpret_cast<float2*>(out_base + (out_is_xz ? 2 : 1) * ut.ring_off);
+    const float2* zin = reinterpret_cast<const float2*>(in_buf + ut.ring_off);
     const int pitch = M2 + 1;
     for (int idx = threadIdx.x; idx < (B << l2); idx += blockDim.x) {
         const int b = idx >> l2, n2 = idx & (M2 - 1);
-        s_fft[b * pitch + bitrev(n2, l2)] = zin[(size_t)(r0 + b) * M2 + n2];
+        const int e = (r0 + b) * M2 + n2;
+        s_fft[b * pitch + bitrev(n2, l2)] = SRC_WAVE ? load_pair(p.wave, p.wave_dtype, ut.wave_off, e, ut.n) : zin[e];
     }
     __syncthreads();
     smem_fft<INV>(s_fft, pitch, l2, B);
     const int logB = 31 - __clz(B);
-    for (int idx = threadIdx.x; idx < (B << l2); idx += blockDim.x) {
-        const int k2 = idx >> logB, b = idx & (B - 1);
-        zout[(size_t)k2 * M1 + r0 + b] = s_fft[b * pitch + k2];
+    if (DST_RING) {
+        float4* ring = reinterpret_cast<float4*>(p.xz + ut.ring_off);
+        for (int idx = threadIdx.x; idx < (B << l2); idx += blockDim.x) {
+            const int k2 = idx >> logB, b = idx & (B - 1);
+            const int m = k2 * M1 + r0 + b;
+            const float2 w = s_fft[b * pitch + k2];
+            const float2 x = load_pair(p.wave, p.wave_dtype, ut.wave_off, m, ut.n);
+            ring[m] = make_float4(x.x, w.x, x.y, w.y);
+        }
+    } else {
+        float2* zout = reinterpret_cast<float2*>(out_buf + ut.ring_off);
+        for (int idx = threadIdx.x; idx < (B << l2); idx += blockDim.x) {
+            const int k2 = idx >> logB, b = idx & (B - 1);
+            zout[(size_t)k2 * M1 + r0 + b] = s_fft[b * pitch + k2];
+        }
     }
 }
 
@@ -174,12 +234,33 @@ __global__ void __launch_bounds__(kFftThreads)
 // scipy.signal.hilbert keeps h[0]=h[N/2]=1, doubles 0<k<N/2, zeroes the rest: the imaginary
 // part of its output has spectrum Y[k] = -i X[k] (0<k<N/2), Y[0]=Y[N/2]=0.  Packed inverse:
 // W[k] = (Y[k]+conj(Y[M-k])) + i e^{+2 pi i k/N} (Y[k]-conj(Y[M-k])), scaled by 1/N.
-__global__ void hilbert_mask_kernel(const UttDesc* utts, float* buf_base, int buf_is_xz) {
+//
+// The same launch tabulates the injection kernel into `gtab` (when non-null):
+// G[tau] = h[l], l = the odd one of (tau-n) mod N2, (tau-n-1) mod N2,
+// h[l] = (2/N2) cot(pi l / N2): the circular Hilbert kernel for even N2 that matches scipy's
+// one-sided mask.
+__global__ void hilbert_mask_kernel(const UttDesc* utts, float* buf, float* gtab) {
     const UttDesc ut = utts[blockIdx.x];
-    const int M = ut.N2 >> 1;
-    if (M < 1) return;
-    float2* Z = reinterpret_cast<float2*>(buf_base + (buf_is_xz ? 2 : 1) * ut.ring_off);
-    const float invN = 1.0f / (float)ut.N2;
+    const int N2 = ut.N2;
+    const int M = N2 >> 1;
+    const float invN = 1.0f / (float)N2;
+    if (gtab) {
+        float* G = gtab + ut.ring_off;
+        for (int tau = blockIdx.y * blockDim.x + threadIdx.x; tau < N2; tau += gridDim.y * blockDim.x) {
+            float g = 0.f;
+            if (N2 > 2) {
+                int l = (tau - ut.n) & (N2 - 1);
+                if (!(l & 1)) l = (l - 1) & (N2 - 1);
+                if (l > N2 / 2) l -= N2;  // cot is odd and pi-periodic: keep |l| <= N2/2 for accuracy
+                float sn, cs;
+                sincospif((float)l * invN, &sn, &cs);
+                g = 2.0f * invN * cs / sn;
+            }
+            G[tau] = g;
+        }
+    }
+    if (!buf || M < 1) return;
+    float2* Z = reinterpret_cast<float2*>(buf + ut.ring_off);
     for (int k = blockIdx.y * blockDim.x + threadIdx.x; k <= M / 2; k += gridDim.y * blockDim.x) {
         if (k == 0) {
             Z[0] = make_float2(0.f, 0.f);
@@ -195,7 +276,7 @@ __global__ void hilbert_mask_kernel(const UttDesc* utts, float* buf_base, int bu
         const float2 ed = cmul(e, dm);
         const float2 Xk = make_float2(0.5f * (sp.x + ed.y), 0.5f * (sp.y - ed.x));  // sp/2 - (i/2) ed
         // X[M-k] = conj(sp)/2 - (i/2) e2 * (-conj(dm)),  e2 = exp(-2 pi i (M-k)/N) = -conj(e)
-        // => X[M-k] = conj(sp)/2 - (i/2) conj(e) conj(dm) = conj(sp)/2 - (i/2) conj(ed)
+        // => X[M-k] = conj(sp)/2 - (i/2) conj(ed)
         const float2 Xm = make_float2(0.5f * (sp.x - ed.y), 0.5f * (-sp.y - ed.x));
         // Y = -i X
         const float2 Yk = make_float2(Xk.y, -Xk.x);
@@ -206,41 +287,24 @@ __global__ void hilbert_mask_kernel(const UttDesc* utts, float* buf_base, int bu
         const float2 ce = make_float2(e.x, -e.y);
         const float2 t2 = cmul(ce, d2);
         const float2 Wk = make_float2((s2.x - t2.y) * invN, (s2.y + t2.x) * invN);
-        // W[M-k] = (Ym + conj(Yk)) + i conj(e2) (Ym - conj(Yk)), conj(e2) = -e
-        //        = conj(s2) + i (-e)(-conj(d2)) = conj(s2) + i e conj(d2) = conj(s2) + i conj(t2)
+        // W[M-k] = conj(s2) + i conj(t2)
         const float2 Wm = make_float2((s2.x + t2.y) * invN, (-s2.y + t2.x) * invN);
         Z[k] = Wk;
         if (k != M - k) Z[M - k] = Wm;
     }
 }
 
-// ---- finish: interleave (x, xi) into the xz ring and tabulate the injection kernel G -------
-// G[tau] = h[l], l = the odd one of (tau-n) mod N2, (tau-n-1) mod N2,
-// h[l] = (2/N2) cot(pi l / N2): the circular Hilbert kernel for even N2 that matches scipy's
-// one-sided mask.
-__global__ void finish_kernel(PrepParams p) {
+// ---- rings without a Hilbert transform: filterbank-only runs (xi = 0) and utterances with
+// N2 <= 2, whose analytic signal is real. -------------------------------------------------
+__global__ void plain_ring_kernel(PrepParams p, int only_tiny) {
     const UttDesc ut = p.utts[blockIdx.x];
     const int N2 = ut.N2;
-    const float* xi = p.Z + ut.ring_off;
-    float2* xz = p.xz + ut.ring_off;
-    float* G = p.G ? p.G + ut.ring_off : nullptr;
-    const float invN = 1.0f / (float)N2;
-    for (int tau = blockIdx.y * blockDim.x + threadIdx.x; tau < N2; tau += gridDim.y * blockDim.x) {
-        const float x = tau < ut.n ? load_wave(p.wave, p.wave_dtype, ut.wave_off + tau) : 0.f;
-        const float im = (p.hilbert && N2 > 2) ? xi[tau] : 0.f;
-        xz[tau] = make_float2(x, im);
-        if (G) {
-            float g = 0.f;
-            if (p.hilbert && N2 > 2) {
-                int l = (tau - ut.n) & (N2 - 1);
-                if (!(l & 1)) l = (l - 1) & (N2 - 1);
-                if (l > N2 / 2) l -= N2;  // cot is odd and pi-periodic: keep |l| <= N2/2 for accuracy
-                float sn, cs;
-                sincospif((float)l * invN, &sn, &cs);
-                g = 2.0f * invN * cs / sn;
-            }
-            G[tau] = g;
-        }
+    if (only_tiny && N2 > 2) return;
+    float4* ring = reinterpret_cast<float4*>(p.xz + ut.ring_off);
+    const int M = N2 > 1 ? N2 >> 1 : 1;  // N2 == 1: one float4 inside the 256-sample allocation
+    for (int m = blockIdx.y * blockDim.x + threadIdx.x; m < M; m += gridDim.y * blockDim.x) {
+        const float2 x = load_pair(p.wave, p.wave_dtype, ut.wave_off, m, ut.n);
+        ring[m] = make_float4(x.x, 0.f, x.y, 0.f);
     }
 }
 
@@ -271,34 +335,40 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
     if (h.n_utts <= 0) return cudaSuccess;
     if (h.max_log2N2 - 1 > 2 * kTwLog) return cudaErrorInvalidValue;
     static bool attr_done = false;
-    const int smem = (kFftSmemPts + 2 * 64 + 64) * (int)sizeof(float2);
+    const int smem = (kFftSmemPts + 256) * (int)sizeof(float2);
     if (!attr_done) {
-        cudaFuncSetAttribute(fft_cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fft_cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fft_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fft_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fft_cols_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fft_cols_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fft_rows_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fft_rows_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fft_rows_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
     const int maxN2 = 1 << h.max_log2N2;
-    const int ew_blocks = (maxN2 / 2 + 1023) / 1024 > 0 ? (maxN2 / 2 + 1023) / 1024 : 1;
-    dim3 g_ew(h.n_utts, ew_blocks > 2048 ? 2048 : ew_blocks);
-    float* Zf = p.Z;
-    float* XZf = reinterpret_cast<float*>(p.xz);
-    if (p.hilbert && h.max_log2N2 >= 2) {
-        pack_kernel<<<g_ew, 256, 0, stream>>>(p);
-        const bool two = (h.max_log2N2 - 1) > kTwLog;
-        dim3 g_cols(h.n_utts, max_blocks(h, true));
-        dim3 g_rows(h.n_utts, max_blocks(h, false));
-        // forward: Z -> (cols in place) -> rows -> XZ (used as scratch)
-        if (two) fft_cols_kernel<false><<<g_cols, kFftThreads, smem, stream>>>(p.utts, Zf, 0);
-        fft_rows_kernel<false><<<g_rows, kFftThreads, smem, stream>>>(p.utts, Zf, 0, XZf, 1);
-        hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, XZf, 1);
-        // inverse: XZ -> (cols in place) -> rows -> Z
-        if (two) fft_cols_kernel<true><<<g_cols, kFftThreads, smem, stream>>>(p.utts, XZf, 1);
-        fft_rows_kernel<true><<<g_rows, kFftThreads, smem, stream>>>(p.utts, XZf, 1, Zf, 0);
+    int ew_blocks = (maxN2 / 2 + 1023) / 1024;
+    ew_blocks = ew_blocks < 1 ? 1 : (ew_blocks > 2048 ? 2048 : ew_blocks);
+    const dim3 g_ew(h.n_utts, ew_blocks);
+    if (!p.hilbert || h.max_log2N2 < 2) {
+        plain_ring_kernel<<<g_ew, 256, 0, stream>>>(p, 0);
+        if (p.G) hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, nullptr, p.G);  // N2 <= 2: G = 0
+        return cudaGetLastError();
     }
-    dim3 g_fin(h.n_utts, ew_blocks > 2048 ? 2048 : ew_blocks);
-    finish_kernel<<<g_fin, 256, 0, stream>>>(p);
+    const bool two = (h.max_log2N2 - 1) > kTwLog;
+    const bool one = h.min_log2N2 - 1 <= kTwLog;  // some utterances take the single-pass path
+    const dim3 g_cols(h.n_utts, max_blocks(h, true));
+    const dim3 g_rows(h.n_utts, max_blocks(h, false));
+    float* A = p.bufA;
+    float* B = p.bufB;
+    // forward
+    if (two) fft_cols_kernel<false, true><<<g_cols, kFftThreads, smem, stream>>>(p, A);
+    if (two) fft_rows_kernel<false, false, false><<<g_rows, kFftThreads, smem, stream>>>(p, A, B);
+    if (one) fft_rows_kernel<false, true, false><<<g_rows, kFftThreads, smem, stream>>>(p, nullptr, B);
+    // Hilbert multiplier in place on B; the injection kernel goes to A (free from here on)
+    hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, B, p.G);
+    // inverse, last pass writes the (x, xi) ring
+    if (two) fft_cols_kernel<true, false><<<g_cols, kFftThreads, smem, stream>>>(p, B);
+    fft_rows_kernel<true, false, true><<<g_rows, kFftThreads, smem, stream>>>(p, B, nullptr);
+    if (h.min_log2N2 < 2) plain_ring_kernel<<<g_ew, 256, 0, stream>>>(p, 1);
     return cudaGetLastError();
 }
 

@@ -13,9 +13,11 @@ struct PrepParams {
     const UttDesc* utts;
     const void* wave;  // flat samples, dtype wave_dtype
     int wave_dtype;
-    float* Z;          // FFT scratch / xi: ring_len floats per utterance
+    float* bufA;       // FFT scratch, ring_len floats per utterance
+    float* bufB;       // FFT scratch, ring_len floats per utterance
     float2* xz;        // out: (x, xi) rings
-    float* G;          // out: injection kernel rings (nullable: not needed for plain Hilbert)
+    float* G;          // out: injection kernel rings; must alias bufA (free once the forward
+                       // transform is done) or be null (plain Hilbert, no table)
     int hilbert;       // 0: filterbank-only run, skip the FFTs and leave xi = 0
 };
 
