@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -12,6 +13,7 @@
 
 #include "../../include/f2cnn_b200.h"
 #include "f2_fused.cuh"
+#include "f2_lanes.cuh"
 #include "f2_post.cuh"
 #include "f2_prep.cuh"
 
@@ -80,12 +82,22 @@ struct f2_plan {
     int C = 0;
     int c_pad = 0;
     float* d_chan = nullptr;
+    std::vector<float> h_chan;  // host copy of the parameter block (for the __constant__ upload)
+    long long id = 0;
     int w_imag = 0, w_edge = 0, w_casc = 0;
     double min_neg_log_r = 0.0;
 };
 
 struct f2_batch {
     f2_plan* plan = nullptr;
+    // lane-stream decomposition (decimated-output path)
+    std::vector<f2::LaneStream> streams;
+    std::vector<char> group_from_zero;  // every stream of the group starts at t0 == 0
+    f2::LaneStream* d_streams = nullptr;
+    f2::LaneGroup* d_groups = nullptr;
+    int n_groups = 0;
+    int groups_w_lpf = -1;  // low-pass warm-up the uploaded group table was built for
+    bool lanes_ok = false;
     int n_utts = 0;
     int step = 1, phase = 0;
     std::vector<f2::UttDesc> utts;
@@ -151,6 +163,9 @@ int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** ou
     }
     f2_plan* p = new (std::nothrow) f2_plan();
     if (!p) return fail(F2_ERR_INVALID, "out of host memory");
+    static long long next_id = 1;
+    p->id = next_id++;
+    p->h_chan = par;
     p->device = device;
     p->C = C;
     p->c_pad = c_pad;
@@ -280,6 +295,58 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
     });
     b->n_items = (long long)items.size();
 
+    // ---- lane streams: (utterance, time chunk), 32 per CTA, kLaneWarps channels per CTA ------
+    {
+        const int tile = f2::lane_tile_samples();
+        const int cb8 = (plan->C + f2::kLaneWarps - 1) / f2::kLaneWarps;
+        long long whole8 = 0;
+        bool sizes_ok = plan->C <= f2::kMaxConstChan;
+        for (int u = 0; u < n_utts; ++u) {
+            if (lengths[u] <= 0) continue;
+            whole8 += cb8;
+            if (b->utts[(size_t)u].N2 < tile) sizes_ok = false;  // ring shorter than a tile
+        }
+        // chunk boundaries on multiples of lcm(tile, step) keep the decimated stores of the
+        // lanes of a warp aligned in time
+        long long align = tile;
+        {
+            long long a = tile, c = step;
+            while (c) { long long r = a % c; a = c; c = r; }
+            const long long l = (long long)tile / a * step;
+            if (l <= 4096) align = l;
+        }
+        long long seg8 = (long long)1 << 40;
+        const long long target_ctas = target_items;  // same meaning: CTAs wanted
+        // split only when whole utterances give less than half the CTAs wanted
+        if (((whole8 / cb8 + 31) / 32) * cb8 * 2 < target_ctas && wave > 0) {
+            // CTAs = ceil(streams/32) * cb8: ask for about target_ctas of them
+            const long long want_streams = std::max<long long>(32, target_ctas * 32 / cb8);
+            seg8 = (long long)align_up((size_t)std::max<long long>(wave / want_streams, 2048), (size_t)align);
+        }
+        for (int u = 0; u < n_utts; ++u) {
+            const int n = b->utts[(size_t)u].n;
+            if (n <= 0) continue;
+            const long long nseg = std::max<long long>(1, (n + seg8 - 1) / seg8);
+            const long long len = (long long)align_up((size_t)((n + nseg - 1) / nseg), (size_t)align);
+            for (long long t0 = 0; t0 < n; t0 += len) {
+                f2::LaneStream st;
+                st.utt = u;
+                st.t0 = (int)t0;
+                st.t1 = (int)std::min<long long>(n, t0 + len);
+                st.pad = 0;
+                b->streams.push_back(st);
+            }
+        }
+        std::stable_sort(b->streams.begin(), b->streams.end(), [](const f2::LaneStream& a, const f2::LaneStream& c) {
+            return (a.t1 - a.t0) > (c.t1 - c.t0);
+        });
+        b->n_groups = (int)((b->streams.size() + 31) / 32);
+        b->group_from_zero.assign((size_t)b->n_groups, 1);
+        for (size_t i = 0; i < b->streams.size(); ++i)
+            if (b->streams[i].t0 != 0) b->group_from_zero[i / 32] = 0;
+        b->lanes_ok = sizes_ok && !b->streams.empty();
+    }
+
     DeviceGuard guard(plan->device);
     cudaError_t e = cudaSuccess;
     if (n_utts > 0) {
@@ -292,9 +359,18 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         if (e == cudaSuccess)
             e = cudaMemcpy(b->d_items, items.data(), sizeof(f2::Item) * items.size(), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && b->lanes_ok) {
+        e = cudaMalloc(&b->d_streams, sizeof(f2::LaneStream) * b->streams.size());
+        if (e == cudaSuccess)
+            e = cudaMemcpy(b->d_streams, b->streams.data(), sizeof(f2::LaneStream) * b->streams.size(),
+                           cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_groups, sizeof(f2::LaneGroup) * (size_t)b->n_groups);
+    }
     if (e != cudaSuccess) {
         if (b->d_utts) cudaFree(b->d_utts);
         if (b->d_items) cudaFree(b->d_items);
+        if (b->d_streams) cudaFree(b->d_streams);
+        if (b->d_groups) cudaFree(b->d_groups);
         delete b;
         return fail(F2_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e));
     }
@@ -307,6 +383,8 @@ int f2_batch_destroy(f2_batch* batch) {
     DeviceGuard guard(batch->plan->device);
     if (batch->d_utts) cudaFree(batch->d_utts);
     if (batch->d_items) cudaFree(batch->d_items);
+    if (batch->d_streams) cudaFree(batch->d_streams);
+    if (batch->d_groups) cudaFree(batch->d_groups);
     delete batch;
     return F2_OK;
 }
@@ -327,9 +405,13 @@ static size_t ws_full_bytes(const f2_batch* b) {
     return align_up((size_t)b->total_samples * (size_t)b->plan->C * sizeof(float), 256);
 }
 
+static size_t ws_edge_bytes(const f2_batch* b) {
+    return align_up((size_t)b->n_utts * (size_t)b->plan->C * 8 * sizeof(float), 256);
+}
+
 size_t f2_batch_workspace_bytes(const f2_batch* b, int want_full_gfb, int want_full_env) {
     if (!b) return 0;
-    size_t s = 4 * ws_ring_bytes(b->total_ring);
+    size_t s = 4 * ws_ring_bytes(b->total_ring) + ws_edge_bytes(b);
     if (want_full_gfb) s += ws_full_bytes(b);
     if (want_full_env) s += ws_full_bytes(b);
     return s + 256;
@@ -364,7 +446,8 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     float* Z = (float*)ws;
     float2* xz = (float2*)(ws + rb);
     float* G = (float*)(ws + 3 * rb);
-    char* cur = ws + 4 * rb;
+    float* edge = (float*)(ws + 4 * rb);
+    char* cur = ws + 4 * rb + ws_edge_bytes(b);
     float* gfb_t = nullptr;
     float* env_t = a->env_t;
     if (want_gfb) {
@@ -391,6 +474,58 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     hp.min_log2N2 = b->min_log2;
     hp.max_log2N2 = b->max_log2;
     F2_CUDA(f2::launch_prep(pp, hp, stream));
+
+    // ---- decimated output only: lane-stream kernel (warp-uniform coefficients) --------------
+    static const bool no_lanes = getenv("F2_NO_LANES") != nullptr;  // development switch
+    if (b->lanes_ok && !no_lanes && a->dec && !a->gfb && !a->env && !a->env_t) {
+        static long long const_owner[64] = {0};
+        const int dev = plan->device;
+        if (dev < 64 && const_owner[dev] != plan->id) {
+            F2_CUDA(f2::upload_lane_constants(plan->h_chan.data(), plan->c_pad, stream));
+            const_owner[dev] = plan->id;
+        } else if (dev >= 64) {
+            F2_CUDA(f2::upload_lane_constants(plan->h_chan.data(), plan->c_pad, stream));
+        }
+        const int tile = f2::lane_tile_samples();
+        const int w_lpf = a->lpf ? (int)align_up((size_t)ceil(log(1e-7) / log(-a1)), (size_t)tile) : 0;
+        if (b->groups_w_lpf != w_lpf) {
+            std::vector<f2::LaneGroup> groups((size_t)b->n_groups);
+            const int w_cold = std::max(plan->w_imag, plan->w_casc);
+            for (int g = 0; g < b->n_groups; ++g) {
+                if (b->group_from_zero[(size_t)g]) {
+                    groups[(size_t)g].mA = groups[(size_t)g].mB = plan->w_imag / tile;  // exact start at t = 0
+                } else {
+                    groups[(size_t)g].mA = w_cold / tile;
+                    groups[(size_t)g].mB = (w_cold + w_lpf) / tile;
+                }
+            }
+            F2_CUDA(cudaMemcpyAsync(b->d_groups, groups.data(), sizeof(f2::LaneGroup) * groups.size(),
+                                    cudaMemcpyHostToDevice, stream));
+            F2_CUDA(cudaStreamSynchronize(stream));  // `groups` is a host temporary
+            b->groups_w_lpf = w_lpf;
+        }
+        F2_CUDA(f2::launch_edge(b->d_utts, b->n_utts, plan->d_chan, plan->C, plan->c_pad, xz, plan->w_edge, edge,
+                                stream));
+        f2::LaneParams lp;
+        lp.utts = b->d_utts;
+        lp.streams = b->d_streams;
+        lp.groups = b->d_groups;
+        lp.n_streams = (int)b->streams.size();
+        lp.xz = xz;
+        lp.G = G;
+        lp.edge = edge;
+        lp.dec = a->dec;
+        lp.C = plan->C;
+        lp.step = b->step;
+        lp.phase = b->phase;
+        lp.lpf = a->lpf ? 1 : 0;
+        lp.lp_k = (float)(-a1);
+        lp.lp_b0 = (float)b0;
+        if (a->ev_fused_start) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_start, stream));
+        F2_CUDA(f2::launch_lanes(lp, b->n_groups, stream));
+        if (a->ev_fused_stop) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_stop, stream));
+        return F2_OK;
+    }
 
     f2::FusedParams fp;
     fp.utts = b->d_utts;

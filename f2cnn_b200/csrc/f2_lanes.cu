@@ -1,0 +1,401 @@
+// f2_lanes.cu -- the decimated-output hot path with warp-uniform coefficients.
+//
+// Same arithmetic as f2_fused.cu (see its header), different mapping.  Measured on B200
+// (tools/rf_probe.cu): an FFMA2 whose three sources are distinct vector registers is capped
+// by register-file operand bandwidth at 66-76 % of the FMA-pipe rate, while an FFMA2 that
+// reads two register pairs plus a UNIFORM-register operand runs at 99 %.  With one thread per
+// channel (f2_fused.cu) the coefficients are per-lane and every FFMA2 pays that tax.  Here
+//   lane  = one stream (an utterance, or a time chunk of one),
+//   warp  = one channel, whose 13 coefficients sit in uniform registers (loaded from
+//           __constant__ memory with an index built from blockIdx and a compile-time warp
+//           number -- the only form ptxas keeps on the uniform datapath),
+//   CTA   = kLaneWarps channels x 32 streams + one producer warp.
+// The producer warp streams tiles of 32 samples of each lane's (x, xi) ring and injection
+// kernel into shared memory with per-lane 1-D TMA bulk copies; full/empty mbarriers make
+// a kLaneStages-deep pipeline, so consumer warps never meet at a CTA-wide barrier.  Rows are
+// padded by 16 bytes so that the per-lane 128-bit shared loads are conflict-free.
+//
+// The edge residuals e_k (zero-padded ring equation at positions n, n+1) are computed once per
+// (utterance, channel) by edge_kernel and read back by every stream of that utterance.
+#include "f2_lanes.cuh"
+
+#include <stdlib.h>
+
+namespace f2 {
+
+constexpr int kLaneTile = 32;     // samples per tile
+constexpr int kLaneStages = 4;    // pipeline depth
+constexpr int kXzPitch = kLaneTile * 8 + 16;  // bytes per lane row of (x, xi)
+constexpr int kGPitch = kLaneTile * 4 + 16;   // bytes per lane row of G
+constexpr int kStageBytes = 32 * (kXzPitch + kGPitch);
+
+__constant__ float c_par[13 * kMaxConstChan];  // [parameter][channel], see ChanPar
+
+cudaError_t upload_lane_constants(const float* host_par, int c_pad, cudaStream_t stream) {
+    // host_par is [kNumChanPar][c_pad]; constant layout is [13][kMaxConstChan]
+    for (int k = 0; k < 13; ++k) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_par, host_par + (size_t)k * c_pad, sizeof(float) * c_pad,
+                                                sizeof(float) * (size_t)k * kMaxConstChan, cudaMemcpyHostToDevice,
+                                                stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- edge residuals ------------------------------------------------------------------------
+// One thread per channel, CTA = (utterance, 128 channels): real cascade over the last w_edge
+// samples from zero state (exact when the utterance is shorter), then
+//   e0 = b1*y[n-1] + b2*y[n-2] - z_k*u[n-1] = (cy-1)*y - cq*q - z_k*u,   e1 = b2*y[n-1] = cq*y
+// in the a0-free stage variables.  Stored parity-resolved: edge[0..3] multiplies G at even t,
+// edge[4..7] at odd t ((t-n) odd -> e0).
+__global__ void __launch_bounds__(kChanPerBlock) edge_kernel(const UttDesc* utts, const float* __restrict__ chan,
+                                                             int C, int c_pad, const float2* __restrict__ xz,
+                                                             int w_edge, float* __restrict__ edge) {
+    const UttDesc ut = utts[blockIdx.x];
+    const int c = blockIdx.y * kChanPerBlock + threadIdx.x;
+    if (c >= C || ut.n <= 0) return;
+    float z[4], cq[4], ncy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        z[i] = chan[(P_Z + i) * c_pad + c];
+        cq[i] = chan[(P_CQ + i) * c_pad + c];
+        ncy[i] = chan[(P_NCY + i) * c_pad + c];
+    }
+    float y[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    float up0 = 0.f;
+    const int n = ut.n;
+    int t0 = n - w_edge;
+    t0 = t0 > 0 ? t0 : 0;
+    const float2* src = xz + ut.ring_off;
+    if (ut.N2 > 2) {
+#pragma unroll 4
+        for (int t = t0; t < n; ++t) {
+            float u = __ldg(&src[t].x);
+            float up = up0;
+            up0 = u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float in = fmaf(z[i], up, u);
+                const float yo = y[i];
+                float qn = fmaf(cq[i], q[i], in);
+                qn = fmaf(ncy[i], yo, qn);
+                const float yn = yo + qn;
+                q[i] = qn;
+                y[i] = yn;
+                up = yo;
+                u = yn;
+            }
+        }
+    }
+    float e0[4], e1[4];
+    float uprev = up0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float cy = -ncy[i];
+        e0[i] = fmaf(cy - 1.0f, y[i], -cq[i] * q[i]) - z[i] * uprev;
+        e1[i] = cq[i] * y[i];
+        uprev = y[i];
+    }
+    if (ut.N2 <= 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e0[i] = e1[i] = 0.f;
+    }
+    const bool n_odd = (n & 1) != 0;
+    float4* o = reinterpret_cast<float4*>(edge + ((size_t)blockIdx.x * C + c) * 8);
+    const float4 even = n_odd ? make_float4(e0[0], e0[1], e0[2], e0[3]) : make_float4(e1[0], e1[1], e1[2], e1[3]);
+    const float4 odd = n_odd ? make_float4(e1[0], e1[1], e1[2], e1[3]) : make_float4(e0[0], e0[1], e0[2], e0[3]);
+    o[0] = even;
+    o[1] = odd;
+}
+
+cudaError_t launch_edge(const UttDesc* utts, int n_utts, const float* chan, int C, int c_pad, const float2* xz,
+                        int w_edge, float* edge, cudaStream_t stream) {
+    if (n_utts <= 0) return cudaSuccess;
+    dim3 grid(n_utts, (C + kChanPerBlock - 1) / kChanPerBlock);
+    edge_kernel<<<grid, kChanPerBlock, 0, stream>>>(utts, chan, C, c_pad, xz, w_edge, edge);
+    return cudaGetLastError();
+}
+
+// ---- lane kernel ---------------------------------------------------------------------------
+struct CoefU {  // warp-uniform
+    float z[4], cq[4], ncy[4], g4;
+};
+
+struct LState {
+    float2 y[4], q[4];
+    float2 up;
+    float l, eprev;
+};
+
+__device__ __forceinline__ float2 cascade_u(const CoefU& k, LState& s, float2 u, float g, const float (&e)[4]) {
+    float2 up = s.up;
+    s.up = u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 in = __ffma2_rn(make_float2(k.z[i], k.z[i]), up, u);
+        in.y = fmaf(e[i], g, in.y);
+        const float2 yo = s.y[i];
+        float2 qn = __ffma2_rn(make_float2(k.cq[i], k.cq[i]), s.q[i], in);
+        qn = __ffma2_rn(make_float2(k.ncy[i], k.ncy[i]), yo, qn);
+        const float2 yn = __fadd2_rn(yo, qn);
+        s.q[i] = qn;
+        s.y[i] = yn;
+        up = yo;
+        u = yn;
+    }
+    return u;
+}
+
+struct LaneOut {
+    float* dec;
+    int next_dec;
+    int t1;
+    int step;
+    size_t C;
+    float scale;
+};
+
+// One tile (32 samples) of one lane.  ENV: 0 cascade only, 1 magnitude, 2 magnitude + low-pass.
+template <int ENV, bool OUT, bool MASKX>
+__device__ __forceinline__ void lane_tile(const CoefU& k, LState& s, const float (&ee)[4], const float (&eo)[4],
+                                          const float4* __restrict__ sx, const float4* __restrict__ sg, int t,
+                                          float xm, float lp_k, LaneOut& o) {
+#pragma unroll 1
+    for (int i = 0; i < kLaneTile; i += 8) {
+        float xv[16], gv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = sx[(i >> 1) + j];
+            xv[4 * j + 0] = v.x;
+            xv[4 * j + 1] = v.y;
+            xv[4 * j + 2] = v.z;
+            xv[4 * j + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float4 v = sg[(i >> 2) + j];
+            gv[4 * j + 0] = v.x;
+            gv[4 * j + 1] = v.y;
+            gv[4 * j + 2] = v.z;
+            gv[4 * j + 3] = v.w;
+        }
+        float ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 u = make_float2(MASKX ? xm * xv[2 * j] : xv[2 * j], xv[2 * j + 1]);
+            const float2 y = (j & 1) ? cascade_u(k, s, u, gv[j], eo) : cascade_u(k, s, u, gv[j], ee);
+            if (ENV > 0) {
+                float e = fast_sqrt(fmaf(y.x, y.x, y.y * y.y));
+                if (ENV == 2) {
+                    s.l = fmaf(lp_k, s.l, e + s.eprev);
+                    s.eprev = e;
+                    e = s.l;
+                }
+                ev[j] = e;
+            }
+        }
+        if (OUT && ENV > 0) {
+            while (o.next_dec < t + i + 8) {
+                const int r = o.next_dec - (t + i);
+                float v = ev[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) v = (r == j) ? ev[j] : v;
+                if (o.next_dec < o.t1) __stcs(o.dec, o.scale * v);
+                o.dec += o.C;
+                o.next_dec += o.step;
+            }
+        }
+    }
+}
+
+struct ConsumerArgs {
+    LaneParams p;
+    unsigned char* smem;
+    uint64_t* full;
+    uint64_t* empty;
+    LaneStream st;
+    long long dec_off;
+    int lane_valid;
+    int M, mA, mB, w_pre;
+};
+
+// __noinline__ on purpose: inlined into a switch over the warp index the eight copies are merged
+// back into one body with a per-thread channel index, and the coefficients land in vector
+// registers.  As separate functions the index is blockIdx.y * kLaneWarps + W: uniform.
+template <int W>
+__device__ __noinline__ void lane_consumer(const ConsumerArgs a) {
+    const LaneParams& p = a.p;
+    unsigned char* smem = a.smem;
+    uint64_t* full = a.full;
+    uint64_t* empty = a.empty;
+    const LaneStream st = a.st;
+    const bool lane_valid = a.lane_valid != 0;
+    const int M = a.M, mA = a.mA, mB = a.mB, w_pre = a.w_pre;
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.y * kLaneWarps + W;  // uniform: blockIdx and a compile-time constant
+    if (ch >= p.C) {
+        // nothing to compute for a channel past the end, but the pipeline still has to turn
+        for (int m = 0; m < M; ++m) {
+            const int b = m % kLaneStages;
+            mbar_wait(&full[b], (uint32_t)((m / kLaneStages) & 1));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[b]);
+        }
+        return;
+    }
+    CoefU k;
+    k.g4 = c_par[P_G4 * kMaxConstChan + ch];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k.z[i] = c_par[(P_Z + i) * kMaxConstChan + ch];
+        k.cq[i] = c_par[(P_CQ + i) * kMaxConstChan + ch];
+        k.ncy[i] = c_par[(P_NCY + i) * kMaxConstChan + ch];
+    }
+    float ee[4], eo[4];
+    {
+        const float4* e = reinterpret_cast<const float4*>(p.edge + ((size_t)st.utt * p.C + ch) * 8);
+        const float4 a = __ldg(e), b = __ldg(e + 1);
+        ee[0] = a.x; ee[1] = a.y; ee[2] = a.z; ee[3] = a.w;
+        eo[0] = b.x; eo[1] = b.y; eo[2] = b.z; eo[3] = b.w;
+    }
+    const int ts = st.t0 - w_pre;
+    LaneOut o;
+    o.C = (size_t)p.C;
+    o.step = p.step;
+    o.t1 = lane_valid ? st.t1 : st.t0;
+    o.scale = p.lpf ? k.g4 * p.lp_b0 : k.g4;
+    {
+        int j0 = 0;
+        if (st.t0 > p.phase) j0 = (st.t0 - p.phase + p.step - 1) / p.step;
+        o.next_dec = p.phase + j0 * p.step;
+        o.dec = p.dec + (size_t)(a.dec_off + j0) * o.C + ch;
+    }
+    LState s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s.y[i] = make_float2(0.f, 0.f);
+        s.q[i] = make_float2(0.f, 0.f);
+    }
+    s.up = make_float2(0.f, 0.f);
+    s.l = 0.f;
+    s.eprev = 0.f;
+
+    for (int m = 0; m < M; ++m) {
+        const int b = m % kLaneStages;
+        mbar_wait(&full[b], (uint32_t)((m / kLaneStages) & 1));
+        const int t = ts + m * kLaneTile;
+        const float4* sx = reinterpret_cast<const float4*>(smem + b * kStageBytes + lane * kXzPitch);
+        const float4* sg = reinterpret_cast<const float4*>(smem + b * kStageBytes + 32 * kXzPitch + lane * kGPitch);
+        if (t == 0) {  // the reference's low-pass starts from zero state at the first sample
+            s.l = 0.f;
+            s.eprev = 0.f;
+        }
+        if (m < mA) {
+            lane_tile<0, false, true>(k, s, ee, eo, sx, sg, t, t >= 0 ? 1.f : 0.f, p.lp_k, o);
+        } else if (m < mB) {
+            lane_tile<2, false, true>(k, s, ee, eo, sx, sg, t, t >= 0 ? 1.f : 0.f, p.lp_k, o);
+        } else if (p.lpf) {
+            lane_tile<2, true, false>(k, s, ee, eo, sx, sg, t, 1.f, p.lp_k, o);
+        } else {
+            lane_tile<1, true, false>(k, s, ee, eo, sx, sg, t, 1.f, p.lp_k, o);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[b]);
+    }
+}
+
+__global__ void __launch_bounds__((kLaneWarps + 1) * 32, 2) lane_kernel(const LaneParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_full[kLaneStages];
+    __shared__ __align__(8) uint64_t s_empty[kLaneStages];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sidx = blockIdx.x * 32 + lane;
+    const bool lane_valid = sidx < p.n_streams;
+    LaneStream st = p.streams[lane_valid ? sidx : 0];
+    if (!lane_valid) st.t1 = st.t0;  // zero-length stream on valid memory
+    const UttDesc ut = p.utts[st.utt];
+    const LaneGroup grp = p.groups[blockIdx.x];
+    const int w_pre = grp.mB * kLaneTile;
+    int len = st.t1 - st.t0;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, off));
+    const int M = (w_pre + len + kLaneTile - 1) / kLaneTile;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kLaneStages; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], kLaneWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kLaneWarps) {
+        // ---- producer: per-lane TMA bulk copies of this lane's ring tiles ----
+        const float2* xz_ring = p.xz + ut.ring_off;
+        const float* g_ring = p.G + ut.ring_off;
+        const int mask = ut.N2 - 1;
+        const int ts = st.t0 - w_pre;
+        for (int m = 0; m < M; ++m) {
+            const int b = m % kLaneStages;
+            if (m >= kLaneStages) mbar_wait(&s_empty[b], (uint32_t)(((m / kLaneStages) - 1) & 1));
+            const int tau = (ts + m * kLaneTile) & mask;
+            if (lane == 0) mbar_expect_tx(&s_full[b], 32 * kLaneTile * 12);
+            __syncwarp();
+            tma_load_1d(smem + b * kStageBytes + lane * kXzPitch, xz_ring + tau, kLaneTile * 8, &s_full[b]);
+            tma_load_1d(smem + b * kStageBytes + 32 * kXzPitch + lane * kGPitch, g_ring + tau, kLaneTile * 4,
+                        &s_full[b]);
+        }
+        return;
+    }
+    // ---- consumers: one specialised copy per warp so that the channel index is uniform ----
+    ConsumerArgs a;
+    a.p = p;
+    a.smem = smem;
+    a.full = s_full;
+    a.empty = s_empty;
+    a.st = st;
+    a.dec_off = ut.dec_off;
+    a.lane_valid = lane_valid ? 1 : 0;
+    a.M = M;
+    a.mA = grp.mA;
+    a.mB = grp.mB;
+    a.w_pre = w_pre;
+    switch (warp) {
+        case 0: lane_consumer<0>(a); break;
+        case 1: lane_consumer<1>(a); break;
+        case 2: lane_consumer<2>(a); break;
+        case 3: lane_consumer<3>(a); break;
+#if F2_LANE_WARPS > 4
+        case 4: lane_consumer<4>(a); break;
+        case 5: lane_consumer<5>(a); break;
+        case 6: lane_consumer<6>(a); break;
+        case 7: lane_consumer<7>(a); break;
+#endif
+        default: break;
+    }
+}
+
+int lane_tile_samples() { return kLaneTile; }
+
+cudaError_t launch_lanes(const LaneParams& p, int n_groups, cudaStream_t stream) {
+    if (n_groups <= 0) return cudaSuccess;
+    static bool attr_done = false;
+    const int smem = kLaneStages * kStageBytes;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid(n_groups, (p.C + kLaneWarps - 1) / kLaneWarps);
+    lane_kernel<<<grid, (kLaneWarps + 1) * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace f2
