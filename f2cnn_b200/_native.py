@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libf2cnn_b200.so")
+LIB_PATH = os.environ.get("F2CNN_B200_LIB") or os.path.join(_HERE, "libf2cnn_b200.so")  # env override: tuning builds
 
 F2_OK = 0
 F2_I16, F2_F32, F2_F64 = 0, 1, 2

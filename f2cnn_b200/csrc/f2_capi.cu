@@ -476,8 +476,11 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     F2_CUDA(f2::launch_prep(pp, hp, stream));
 
     // ---- decimated output only: lane-stream kernel (warp-uniform coefficients) --------------
-    static const bool no_lanes = getenv("F2_NO_LANES") != nullptr;  // development switch
-    if (b->lanes_ok && !no_lanes && a->dec && !a->gfb && !a->env && !a->env_t) {
+    // Experimental (off by default, F2_USE_LANES=1): measured equal to the thread-per-channel
+    // kernel (47.6 vs 47.0 ms on config 2) because ptxas keeps only a third of the coefficients
+    // on the uniform datapath and the per-warp code copies press on the instruction cache.
+    static const bool use_lanes = getenv("F2_USE_LANES") != nullptr;
+    if (b->lanes_ok && use_lanes && a->dec && !a->gfb && !a->env && !a->env_t) {
         static long long const_owner[64] = {0};
         const int dev = plan->device;
         if (dev < 64 && const_owner[dev] != plan->id) {

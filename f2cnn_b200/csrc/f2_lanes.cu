@@ -23,6 +23,10 @@
 
 namespace f2 {
 
+#ifndef F2_LANE_UNROLL
+#define F2_LANE_UNROLL 8
+#endif
+constexpr int kLaneU = F2_LANE_UNROLL;  // samples per inner-loop iteration (code size vs loop overhead)
 constexpr int kLaneTile = 32;     // samples per tile
 constexpr int kLaneStages = 4;    // pipeline depth
 constexpr int kXzPitch = kLaneTile * 8 + 16;  // bytes per lane row of (x, xi)
@@ -159,91 +163,49 @@ struct LaneOut {
     float scale;
 };
 
-// One tile (32 samples) of one lane.  ENV: 0 cascade only, 1 magnitude, 2 magnitude + low-pass.
-template <int ENV, bool OUT, bool MASKX>
-__device__ __forceinline__ void lane_tile(const CoefU& k, LState& s, const float (&ee)[4], const float (&eo)[4],
-                                          const float4* __restrict__ sx, const float4* __restrict__ sg, int t,
-                                          float xm, float lp_k, LaneOut& o) {
-#pragma unroll 1
-    for (int i = 0; i < kLaneTile; i += 8) {
-        float xv[16], gv[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 v = sx[(i >> 1) + j];
-            xv[4 * j + 0] = v.x;
-            xv[4 * j + 1] = v.y;
-            xv[4 * j + 2] = v.z;
-            xv[4 * j + 3] = v.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float4 v = sg[(i >> 2) + j];
-            gv[4 * j + 0] = v.x;
-            gv[4 * j + 1] = v.y;
-            gv[4 * j + 2] = v.z;
-            gv[4 * j + 3] = v.w;
-        }
-        float ev[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float2 u = make_float2(MASKX ? xm * xv[2 * j] : xv[2 * j], xv[2 * j + 1]);
-            const float2 y = (j & 1) ? cascade_u(k, s, u, gv[j], eo) : cascade_u(k, s, u, gv[j], ee);
-            if (ENV > 0) {
-                float e = fast_sqrt(fmaf(y.x, y.x, y.y * y.y));
-                if (ENV == 2) {
-                    s.l = fmaf(lp_k, s.l, e + s.eprev);
-                    s.eprev = e;
-                    e = s.l;
-                }
-                ev[j] = e;
-            }
-        }
-        if (OUT && ENV > 0) {
-            while (o.next_dec < t + i + 8) {
-                const int r = o.next_dec - (t + i);
-                float v = ev[0];
-#pragma unroll
-                for (int j = 1; j < 8; ++j) v = (r == j) ? ev[j] : v;
-                if (o.next_dec < o.t1) __stcs(o.dec, o.scale * v);
-                o.dec += o.C;
-                o.next_dec += o.step;
-            }
-        }
-    }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 
-struct ConsumerArgs {
-    LaneParams p;
-    unsigned char* smem;
-    uint64_t* full;
-    uint64_t* empty;
-    LaneStream st;
-    long long dec_off;
-    int lane_valid;
-    int M, mA, mB, w_pre;
-};
-
-// __noinline__ on purpose: inlined into a switch over the warp index the eight copies are merged
-// back into one body with a per-thread channel index, and the coefficients land in vector
-// registers.  As separate functions the index is blockIdx.y * kLaneWarps + W: uniform.
-template <int W>
-__device__ __noinline__ void lane_consumer(const ConsumerArgs a) {
-    const LaneParams& p = a.p;
-    unsigned char* smem = a.smem;
-    uint64_t* full = a.full;
-    uint64_t* empty = a.empty;
-    const LaneStream st = a.st;
-    const bool lane_valid = a.lane_valid != 0;
-    const int M = a.M, mA = a.mA, mB = a.mB, w_pre = a.w_pre;
+// One specialised copy per consumer warp so that the channel index -- blockIdx.x * kLaneWarps
+// + W -- is uniform and the coefficients come from uniform registers.  __noinline__ on purpose:
+// inlined into a switch over the warp index the copies are merged back into one body with a
+// per-thread channel index and the coefficients land in vector registers.  The copies share
+// the instruction cache, so each is kept to ONE small loop: every tile runs the same body (x
+// masked to zero before t = 0, envelope and low-pass always computed, stores predicated on
+// being past the warm-up).  All arguments are scalars (registers), shared memory is addressed
+// with 32-bit shared-window addresses.
+template <int W, bool LPF>
+__device__ __noinline__ void lane_consumer(const uint32_t smem, const uint32_t full, const uint32_t empty,
+                                           const float* __restrict__ edge_utt, float* __restrict__ dec_base,
+                                           const int ts, const int t1, const int M, const int mB, const int step,
+                                           const int dec0, const int C, const float lp_k, const float lp_b0) {
     const int lane = threadIdx.x & 31;
-    const int ch = blockIdx.y * kLaneWarps + W;  // uniform: blockIdx and a compile-time constant
-    if (ch >= p.C) {
+    const int ch = blockIdx.x * kLaneWarps + W;
+    if (ch >= C) {
         // nothing to compute for a channel past the end, but the pipeline still has to turn
         for (int m = 0; m < M; ++m) {
             const int b = m % kLaneStages;
-            mbar_wait(&full[b], (uint32_t)((m / kLaneStages) & 1));
+            mbar_wait_a(full + 8 * b, (uint32_t)((m / kLaneStages) & 1));
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[b]);
+            if (lane == 0) mbar_arrive_a(empty + 8 * b);
         }
         return;
     }
@@ -257,23 +219,14 @@ __device__ __noinline__ void lane_consumer(const ConsumerArgs a) {
     }
     float ee[4], eo[4];
     {
-        const float4* e = reinterpret_cast<const float4*>(p.edge + ((size_t)st.utt * p.C + ch) * 8);
-        const float4 a = __ldg(e), b = __ldg(e + 1);
-        ee[0] = a.x; ee[1] = a.y; ee[2] = a.z; ee[3] = a.w;
-        eo[0] = b.x; eo[1] = b.y; eo[2] = b.z; eo[3] = b.w;
+        const float4* e = reinterpret_cast<const float4*>(edge_utt + (size_t)ch * 8);
+        const float4 v0 = __ldg(e), v1 = __ldg(e + 1);
+        ee[0] = v0.x; ee[1] = v0.y; ee[2] = v0.z; ee[3] = v0.w;
+        eo[0] = v1.x; eo[1] = v1.y; eo[2] = v1.z; eo[3] = v1.w;
     }
-    const int ts = st.t0 - w_pre;
-    LaneOut o;
-    o.C = (size_t)p.C;
-    o.step = p.step;
-    o.t1 = lane_valid ? st.t1 : st.t0;
-    o.scale = p.lpf ? k.g4 * p.lp_b0 : k.g4;
-    {
-        int j0 = 0;
-        if (st.t0 > p.phase) j0 = (st.t0 - p.phase + p.step - 1) / p.step;
-        o.next_dec = p.phase + j0 * p.step;
-        o.dec = p.dec + (size_t)(a.dec_off + j0) * o.C + ch;
-    }
+    const float scale = LPF ? k.g4 * lp_b0 : k.g4;
+    int next_dec = 1 << 30;  // armed when the warm-up is over
+    float* dec = dec_base + ch;
     LState s;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -283,28 +236,65 @@ __device__ __noinline__ void lane_consumer(const ConsumerArgs a) {
     s.up = make_float2(0.f, 0.f);
     s.l = 0.f;
     s.eprev = 0.f;
+    const uint32_t row_x = smem + lane * kXzPitch;
+    const uint32_t row_g = smem + 32 * kXzPitch + lane * kGPitch;
 
     for (int m = 0; m < M; ++m) {
         const int b = m % kLaneStages;
-        mbar_wait(&full[b], (uint32_t)((m / kLaneStages) & 1));
+        mbar_wait_a(full + 8 * b, (uint32_t)((m / kLaneStages) & 1));
         const int t = ts + m * kLaneTile;
-        const float4* sx = reinterpret_cast<const float4*>(smem + b * kStageBytes + lane * kXzPitch);
-        const float4* sg = reinterpret_cast<const float4*>(smem + b * kStageBytes + 32 * kXzPitch + lane * kGPitch);
-        if (t == 0) {  // the reference's low-pass starts from zero state at the first sample
+        const uint32_t sx = row_x + b * kStageBytes;
+        const uint32_t sg = row_g + b * kStageBytes;
+        const float xm = t >= 0 ? 1.f : 0.f;  // the real path sees zeros before the first sample
+        if (t == 0) {                         // the reference's low-pass starts from zero state at t = 0
             s.l = 0.f;
             s.eprev = 0.f;
         }
-        if (m < mA) {
-            lane_tile<0, false, true>(k, s, ee, eo, sx, sg, t, t >= 0 ? 1.f : 0.f, p.lp_k, o);
-        } else if (m < mB) {
-            lane_tile<2, false, true>(k, s, ee, eo, sx, sg, t, t >= 0 ? 1.f : 0.f, p.lp_k, o);
-        } else if (p.lpf) {
-            lane_tile<2, true, false>(k, s, ee, eo, sx, sg, t, 1.f, p.lp_k, o);
-        } else {
-            lane_tile<1, true, false>(k, s, ee, eo, sx, sg, t, 1.f, p.lp_k, o);
+        if (m == mB) next_dec = dec0;
+#pragma unroll 1
+        for (int i = 0; i < kLaneTile; i += kLaneU) {
+            float xv[2 * kLaneU], gv[kLaneU];
+#pragma unroll
+            for (int j = 0; j < kLaneU / 2; ++j) {
+                const float4 v = lds128(sx + 8 * i + 16 * j);
+                xv[4 * j + 0] = v.x;
+                xv[4 * j + 1] = v.y;
+                xv[4 * j + 2] = v.z;
+                xv[4 * j + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < kLaneU / 4; ++j) {
+                const float4 v = lds128(sg + 4 * i + 16 * j);
+                gv[4 * j + 0] = v.x;
+                gv[4 * j + 1] = v.y;
+                gv[4 * j + 2] = v.z;
+                gv[4 * j + 3] = v.w;
+            }
+            float ev[kLaneU];
+#pragma unroll
+            for (int j = 0; j < kLaneU; ++j) {
+                const float2 u = make_float2(xm * xv[2 * j], xv[2 * j + 1]);
+                const float2 y = (j & 1) ? cascade_u(k, s, u, gv[j], eo) : cascade_u(k, s, u, gv[j], ee);
+                float e = fast_sqrt(fmaf(y.x, y.x, y.y * y.y));
+                if (LPF) {
+                    s.l = fmaf(lp_k, s.l, e + s.eprev);
+                    s.eprev = e;
+                    e = s.l;
+                }
+                ev[j] = e;
+            }
+            while (next_dec < t + i + kLaneU) {
+                const int r = next_dec - (t + i);
+                float v = ev[0];
+#pragma unroll
+                for (int j = 1; j < kLaneU; ++j) v = (r == j) ? ev[j] : v;
+                if (next_dec < t1) __stcs(dec, scale * v);
+                dec += C;
+                next_dec += step;
+            }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[b]);
+        if (lane == 0) mbar_arrive_a(empty + 8 * b);
     }
 }
 
@@ -315,12 +305,12 @@ __global__ void __launch_bounds__((kLaneWarps + 1) * 32, 2) lane_kernel(const La
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int sidx = blockIdx.x * 32 + lane;
+    const int sidx = blockIdx.y * 32 + lane;
     const bool lane_valid = sidx < p.n_streams;
     LaneStream st = p.streams[lane_valid ? sidx : 0];
     if (!lane_valid) st.t1 = st.t0;  // zero-length stream on valid memory
     const UttDesc ut = p.utts[st.utt];
-    const LaneGroup grp = p.groups[blockIdx.x];
+    const LaneGroup grp = p.groups[blockIdx.y];
     const int w_pre = grp.mB * kLaneTile;
     int len = st.t1 - st.t0;
 #pragma unroll
@@ -355,31 +345,38 @@ __global__ void __launch_bounds__((kLaneWarps + 1) * 32, 2) lane_kernel(const La
         return;
     }
     // ---- consumers: one specialised copy per warp so that the channel index is uniform ----
-    ConsumerArgs a;
-    a.p = p;
-    a.smem = smem;
-    a.full = s_full;
-    a.empty = s_empty;
-    a.st = st;
-    a.dec_off = ut.dec_off;
-    a.lane_valid = lane_valid ? 1 : 0;
-    a.M = M;
-    a.mA = grp.mA;
-    a.mB = grp.mB;
-    a.w_pre = w_pre;
+    // per-lane scalars for the consumer
+    const int ts = st.t0 - w_pre;
+    const int t1 = lane_valid ? st.t1 : st.t0;
+    int j0 = 0;
+    if (st.t0 > p.phase) j0 = (st.t0 - p.phase + p.step - 1) / p.step;
+    const int dec0 = p.phase + j0 * p.step;
+    float* dec_base = p.dec + (size_t)(ut.dec_off + j0) * (size_t)p.C;
+    const float* edge_utt = p.edge + (size_t)st.utt * (size_t)p.C * 8;
+    const uint32_t sm = smem_u32(smem), fu = smem_u32(s_full), em = smem_u32(s_empty);
+#define F2_LANE_CASE(W)                                                                                          \
+    case W:                                                                                                      \
+        if (p.lpf)                                                                                               \
+            lane_consumer<W, true>(sm, fu, em, edge_utt, dec_base, ts, t1, M, grp.mB, p.step, dec0, p.C, p.lp_k, \
+                                   p.lp_b0);                                                                     \
+        else                                                                                                     \
+            lane_consumer<W, false>(sm, fu, em, edge_utt, dec_base, ts, t1, M, grp.mB, p.step, dec0, p.C, p.lp_k, \
+                                    p.lp_b0);                                                                    \
+        break;
     switch (warp) {
-        case 0: lane_consumer<0>(a); break;
-        case 1: lane_consumer<1>(a); break;
-        case 2: lane_consumer<2>(a); break;
-        case 3: lane_consumer<3>(a); break;
+        F2_LANE_CASE(0)
+        F2_LANE_CASE(1)
+        F2_LANE_CASE(2)
+        F2_LANE_CASE(3)
 #if F2_LANE_WARPS > 4
-        case 4: lane_consumer<4>(a); break;
-        case 5: lane_consumer<5>(a); break;
-        case 6: lane_consumer<6>(a); break;
-        case 7: lane_consumer<7>(a); break;
+        F2_LANE_CASE(4)
+        F2_LANE_CASE(5)
+        F2_LANE_CASE(6)
+        F2_LANE_CASE(7)
 #endif
         default: break;
     }
+#undef F2_LANE_CASE
 }
 
 int lane_tile_samples() { return kLaneTile; }
@@ -393,7 +390,7 @@ cudaError_t launch_lanes(const LaneParams& p, int n_groups, cudaStream_t stream)
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    dim3 grid(n_groups, (p.C + kLaneWarps - 1) / kLaneWarps);
+    dim3 grid((p.C + kLaneWarps - 1) / kLaneWarps, n_groups);  // x: the channel blocks of one group run together (L2)
     lane_kernel<<<grid, (kLaneWarps + 1) * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -4,7 +4,7 @@
 #include "f2_common.cuh"
 
 #ifndef F2_LANE_WARPS
-#define F2_LANE_WARPS 8
+#define F2_LANE_WARPS 4
 #endif
 
 namespace f2 {
