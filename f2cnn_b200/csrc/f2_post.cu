@@ -70,10 +70,37 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long lon
     }
 }
 
+// 16-byte version (C % 4 == 0, 16-byte aligned buffers): one warp per window row group, each
+// thread moves float4s; stride-1 windows are `dots` consecutive source rows = one contiguous run.
+__global__ void gather_rows_vec_kernel(const float4* __restrict__ src, const long long* __restrict__ base,
+                                       long long n_rows, int dots, long long stride, int C4,
+                                       float4* __restrict__ out) {
+    const int total = dots * C4;
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const long long b = base[row];
+        float4* o = out + (size_t)row * total;
+        if (stride == 1) {
+            const float4* s = src + (size_t)b * C4;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) __stcs(o + i, __ldg(s + i));
+        } else {
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const int j = i / C4, c = i - j * C4;
+                __stcs(o + i, __ldg(src + (size_t)(b + (long long)j * stride) * C4 + c));
+            }
+        }
+    }
+}
+
 cudaError_t launch_gather_rows(const float* src, const long long* base, long long n_rows, int dots,
                                long long stride, int C, float* out, cudaStream_t stream) {
     if (n_rows <= 0) return cudaSuccess;
-    gather_rows_kernel<<<(unsigned)n_rows, 256, 0, stream>>>(src, base, dots, stride, C, out);
+    if (C % 4 == 0 && ((size_t)src % 16 == 0) && ((size_t)out % 16 == 0)) {
+        const long long blocks = n_rows < 148 * 32 ? n_rows : 148 * 32;
+        gather_rows_vec_kernel<<<(unsigned)blocks, 128, 0, stream>>>((const float4*)src, base, n_rows, dots, stride,
+                                                                     C / 4, (float4*)out);
+    } else {
+        gather_rows_kernel<<<(unsigned)n_rows, 256, 0, stream>>>(src, base, dots, stride, C, out);
+    }
     return cudaGetLastError();
 }
 

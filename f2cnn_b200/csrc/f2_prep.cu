@@ -23,7 +23,7 @@
 namespace f2 {
 
 constexpr int kFftThreads = 256;
-constexpr int kFftSmemPts = 8192;  // complex points per CTA
+constexpr int kFftSmemPts = 4096;  // complex points per CTA (33 KB + swizzle padding: 6 CTAs per SM)
 constexpr int kTwLog = 12;         // twiddle table covers legs up to 4096 points
 
 __device__ float2 g_twiddle[1 << (kTwLog - 1)];  // exp(-2*pi*i*j/4096), j < 2048
@@ -41,6 +41,10 @@ cudaError_t init_twiddles(cudaStream_t stream) {
     init_twiddle_kernel<<<(1 << (kTwLog - 1)) / 256, 256, 0, stream>>>();
     return cudaGetLastError();
 }
+
+// Shared-memory index swizzle: one float2 of padding per 16 keeps the strided accesses of the
+// first radix-4 steps (stride 4 and 16 elements) off the same banks.
+__host__ __device__ __forceinline__ int sw(int i) { return i + (i >> 4); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -92,24 +96,25 @@ __device__ __forceinline__ void smem_fft(float2* s, int pitch, int logL, int bat
             const int j = bf & (per - 1);
             const int pos = j & (h - 1);
             const int i0 = ((j >> st) << (st + 2)) + pos;
-            float2* a = s + arr * pitch + i0;
+            float2* a = s + arr * pitch;
+            const int j0 = sw(i0), j1 = sw(i0 + h), j2 = sw(i0 + 2 * h), j3 = sw(i0 + 3 * h);
             float2 w1 = g_twiddle[pos << (kTwLog - 1 - st)];  // w_{2h}^pos
             float2 w2 = g_twiddle[pos << (kTwLog - 2 - st)];  // w_{4h}^pos
             if (INV) {
                 w1.y = -w1.y;
                 w2.y = -w2.y;
             }
-            const float2 x0 = a[0], x1 = cmul(a[h], w1), x2 = a[2 * h], x3 = cmul(a[3 * h], w1);
+            const float2 x0 = a[j0], x1 = cmul(a[j1], w1), x2 = a[j2], x3 = cmul(a[j3], w1);
             const float2 p0 = cadd(x0, x1), p1 = csub(x0, x1);  // stage st: (0,1)
             const float2 q0 = cadd(x2, x3), q1 = csub(x2, x3);  //           (2,3)
             // stage st+1: (p0,q0) with w2; (p1,q1) with w2 * w_{4h}^h = w2 * (-i) fwd / (+i) inv
             const float2 t0 = cmul(q0, w2);
             const float2 t1r = cmul(q1, w2);
             const float2 t1 = INV ? make_float2(-t1r.y, t1r.x) : make_float2(t1r.y, -t1r.x);
-            a[0] = cadd(p0, t0);
-            a[2 * h] = csub(p0, t0);
-            a[h] = cadd(p1, t1);
-            a[3 * h] = csub(p1, t1);
+            a[j0] = cadd(p0, t0);
+            a[j2] = csub(p0, t0);
+            a[j1] = cadd(p1, t1);
+            a[j3] = csub(p1, t1);
         }
         __syncthreads();
     }
@@ -125,10 +130,11 @@ __device__ __forceinline__ void smem_fft(float2* s, int pitch, int logL, int bat
             float2* a = s + arr * pitch;
             float2 w = g_twiddle[pos << (kTwLog - 1 - st)];
             if (INV) w.y = -w.y;
-            const float2 u = a[i0];
-            const float2 v = cmul(a[i0 + half], w);
-            a[i0] = cadd(u, v);
-            a[i0 + half] = csub(u, v);
+            const int j0 = sw(i0), j1 = sw(i0 + half);
+            const float2 u = a[j0];
+            const float2 v = cmul(a[j1], w);
+            a[j0] = cadd(u, v);
+            a[j1] = csub(u, v);
         }
         __syncthreads();
     }
@@ -163,12 +169,13 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(PrepParams p, flo
     const int c0 = blockIdx.y * B;
     if (c0 >= M2) return;
     float2* z = reinterpret_cast<float2*>(buf + ut.ring_off);
-    const int pitch = M1 + 1;
+    const int pitch = sw(M1) + 1;
     const int logB = 31 - __clz(B);
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < (B << l1); idx += blockDim.x) {
         const int n1 = idx >> logB, b = idx & (B - 1);
         const int e = n1 * M2 + c0 + b;
-        s_fft[b * pitch + bitrev(n1, l1)] = SRC_WAVE ? load_pair(p.wave, p.wave_dtype, ut.wave_off, e, ut.n) : z[e];
+        s_fft[b * pitch + sw(bitrev(n1, l1))] = SRC_WAVE ? load_pair(p.wave, p.wave_dtype, ut.wave_off, e, ut.n) : z[e];
     }
     __syncthreads();
     smem_fft<INV>(s_fft, pitch, l1, B);
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(PrepParams p, flo
         const int n2 = c0 + b;
         float sn, cs;
         sincospif(sgn * (float)(n2 * k1) * invM, &sn, &cs);  // n2*k1 < M <= 2^24: exact in float
-        z[(size_t)k1 * M2 + n2] = cmul(s_fft[b * pitch + k1], make_float2(cs, sn));
+        z[(size_t)k1 * M2 + n2] = cmul(s_fft[b * pitch + sw(k1)], make_float2(cs, sn));
     }
 }
 
@@ -202,11 +209,12 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(PrepParams p, con
     const int r0 = blockIdx.y * B;
     if (r0 >= M1) return;
     const float2* zin = reinterpret_cast<const float2*>(in_buf + ut.ring_off);
-    const int pitch = M2 + 1;
+    const int pitch = sw(M2) + 1;
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < (B << l2); idx += blockDim.x) {
         const int b = idx >> l2, n2 = idx & (M2 - 1);
         const int e = (r0 + b) * M2 + n2;
-        s_fft[b * pitch + bitrev(n2, l2)] = SRC_WAVE ? load_pair(p.wave, p.wave_dtype, ut.wave_off, e, ut.n) : zin[e];
+        s_fft[b * pitch + sw(bitrev(n2, l2))] = SRC_WAVE ? load_pair(p.wave, p.wave_dtype, ut.wave_off, e, ut.n) : zin[e];
     }
     __syncthreads();
     smem_fft<INV>(s_fft, pitch, l2, B);
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(PrepParams p, con
         for (int idx = threadIdx.x; idx < (B << l2); idx += blockDim.x) {
             const int k2 = idx >> logB, b = idx & (B - 1);
             const int m = k2 * M1 + r0 + b;
-            const float2 w = s_fft[b * pitch + k2];
+            const float2 w = s_fft[b * pitch + sw(k2)];
             const float2 x = load_pair(p.wave, p.wave_dtype, ut.wave_off, m, ut.n);
             ring[m] = make_float4(x.x, w.x, x.y, w.y);
         }
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(PrepParams p, con
         float2* zout = reinterpret_cast<float2*>(out_buf + ut.ring_off);
         for (int idx = threadIdx.x; idx < (B << l2); idx += blockDim.x) {
             const int k2 = idx >> logB, b = idx & (B - 1);
-            zout[(size_t)k2 * M1 + r0 + b] = s_fft[b * pitch + k2];
+            zout[(size_t)k2 * M1 + r0 + b] = s_fft[b * pitch + sw(k2)];
         }
     }
 }
@@ -335,7 +343,7 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
     if (h.n_utts <= 0) return cudaSuccess;
     if (h.max_log2N2 - 1 > 2 * kTwLog) return cudaErrorInvalidValue;
     static bool attr_done = false;
-    const int smem = (kFftSmemPts + 256) * (int)sizeof(float2);
+    const int smem = (kFftSmemPts + kFftSmemPts / 16 + 512) * (int)sizeof(float2);
     if (!attr_done) {
         cudaFuncSetAttribute(fft_cols_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_cols_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

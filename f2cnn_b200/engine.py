@@ -236,6 +236,89 @@ def dense_frames(env_t_dev, dots, step, i0, i1, normalize=False, out_dtype=torch
     return out, flag
 
 
+class WindowPipeline:
+    """Host waves in, host (N, 2R+1, C) float32 windows out, for a whole corpus.
+
+    The utterances are cut into `n_sub` contiguous sub-batches; while sub-batch i is being
+    filtered on the compute stream, the windows of sub-batch i-1 travel to the host on a copy
+    stream (double-buffered device output), and the waves of sub-batch i+1 come in on a third
+    stream.  PCIe is the bottleneck of this path (the window tensor is 11x the decimated
+    envelope), so hiding the 50-odd ms of compute behind the D2H copy is what matters.
+
+    bases[u]: int64 array, for every window of utterance u the index (within the utterance)
+    of its FIRST decimated frame; windows are `dots` consecutive frames (on-grid labels)."""
+
+    def __init__(self, plan, lengths, bases, dots=11, step=160, phase=0, lpf=True, cutoff=50, n_sub=8):
+        self.plan, self.dots, self.lpf, self.cutoff = plan, int(dots), bool(lpf), cutoff
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        U = int(lengths.shape[0])
+        n_sub = max(1, min(int(n_sub), U))
+        cum = np.concatenate([[0], np.cumsum(lengths)])
+        cuts = [int(np.searchsorted(cum, cum[-1] * k / n_sub)) for k in range(n_sub + 1)]
+        cuts[0], cuts[-1] = 0, U
+        cuts = sorted(set(cuts))
+        dev = plan.device
+        self.subs = []
+        row = 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            batch = plan.batch(lengths[a:b], step=step, phase=phase)
+            base = np.concatenate([batch.frame_offsets[u - a] + np.asarray(bases[u], dtype=np.int64)
+                                   for u in range(a, b)] + [np.zeros(0, dtype=np.int64)])
+            self.subs.append(dict(batch=batch, base=torch.from_numpy(base).to(dev), s0=int(cum[a]), s1=int(cum[b]),
+                                  r0=row, r1=row + int(base.shape[0])))
+            row += int(base.shape[0])
+        self.n_windows = row
+        C = plan.n_channels
+        max_s = max(s["s1"] - s["s0"] for s in self.subs)
+        max_w = max(s["r1"] - s["r0"] for s in self.subs)
+        max_f = max(s["batch"].total_frames for s in self.subs)
+        self._wave = [None, None]
+        self._max_s = max_s
+        self._win = [torch.empty((max(max_w, 1), self.dots, C), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._dec = torch.empty((max(max_f, 1), C), dtype=torch.float32, device=dev)
+        self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self._ev_in = [torch.cuda.Event() for _ in range(2)]
+        self._ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._ev_free = [torch.cuda.Event() for _ in range(2)]
+        self._ev_wave_free = [torch.cuda.Event() for _ in range(2)]
+
+    def run(self, wave_host, out_host):
+        """wave_host: flat (pinned) host tensor of all samples; out_host: (N, dots, C) float32
+        host tensor (pinned for full speed).  Returns after everything has landed."""
+        comp = torch.cuda.current_stream()
+        dev = self.plan.device
+        for k in range(2):
+            if self._wave[k] is None or self._wave[k].dtype != wave_host.dtype:
+                self._wave[k] = torch.empty(self._max_s, dtype=wave_host.dtype, device=dev)
+        self._s_in.wait_stream(comp)
+        self._s_out.wait_stream(comp)
+        for i, sub in enumerate(self.subs):
+            k = i & 1
+            n_s = sub["s1"] - sub["s0"]
+            with torch.cuda.stream(self._s_in):
+                if i >= 2:
+                    self._s_in.wait_event(self._ev_wave_free[k])
+                self._wave[k][:n_s].copy_(wave_host[sub["s0"]:sub["s1"]], non_blocking=True)
+                self._ev_in[k].record(self._s_in)
+            comp.wait_event(self._ev_in[k])
+            if i >= 2:
+                comp.wait_event(self._ev_free[k])  # the D2H of sub-batch i-2 has drained this buffer
+            n_w = sub["r1"] - sub["r0"]
+            sub["batch"].run(self._wave[k][:n_s], lpf=self.lpf, cutoff=self.cutoff,
+                             out={"dec": self._dec[:max(sub["batch"].total_frames, 1)]})
+            self._ev_wave_free[k].record(comp)
+            if n_w:
+                gather_windows(self._dec, sub["base"], self.dots, 1, out=self._win[k][:n_w])
+            self._ev_done[k].record(comp)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(self._ev_done[k])
+                if n_w:
+                    out_host[sub["r0"]:sub["r1"]].copy_(self._win[k][:n_w], non_blocking=True)
+                self._ev_free[k].record(self._s_out)
+        comp.wait_stream(self._s_out)
+        return out_host
+
+
 # ---- plan cache for the numpy-in / numpy-out drop-in functions -----------------------------
 _plans = {}
 _plans_lock = threading.Lock()
