@@ -261,7 +261,8 @@ class WindowPipeline:
         self.subs = []
         row = 0
         for a, b in zip(cuts[:-1], cuts[1:]):
-            batch = plan.batch(lengths[a:b], step=step, phase=phase)
+            # whole utterances only (target_items=1): same arithmetic as one big batch, bit for bit
+            batch = plan.batch(lengths[a:b], step=step, phase=phase, target_items=1)
             base = np.concatenate([batch.frame_offsets[u - a] + np.asarray(bases[u], dtype=np.int64)
                                    for u in range(a, b)] + [np.zeros(0, dtype=np.int64)])
             self.subs.append(dict(batch=batch, base=torch.from_numpy(base).to(dev), s0=int(cum[a]), s1=int(cum[b]),
