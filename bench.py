@@ -111,6 +111,12 @@ def cpu_arm(coefs, lengths, seed, seconds, steps=1, warmup=0):
     from f2cnn_b200 import synth
     from oracle import oracle as orc
     orc.lib()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core it may run on
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    orc.set_num_threads(avail)
     cores = orc.num_threads()
     rng = np.random.default_rng(seed)
     order = rng.permutation(len(lengths))
