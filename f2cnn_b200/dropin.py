@@ -7,6 +7,7 @@ install() registers this package's drop-in modules in sys.modules under the refe
 module paths:
     gammatone, gammatone.filters
     scripts.processing.GammatoneFiltering / EnvelopeExtraction / InputGenerator
+    scripts.CNN.Evaluating   (GPU front end; model prediction and plots stay the reference's)
 Everything else under `scripts` (LabelDataGenerator, CNN, plotting, readers ...) keeps
 resolving to the reference tree, which must be importable (on sys.path) if those are used.
 Modules of the reference that were imported BEFORE install() and bound hot-path functions by
@@ -22,16 +23,11 @@ _MODULES = {
     "scripts.processing.GammatoneFiltering": "f2cnn_b200.scripts.processing.GammatoneFiltering",
     "scripts.processing.EnvelopeExtraction": "f2cnn_b200.scripts.processing.EnvelopeExtraction",
     "scripts.processing.InputGenerator": "f2cnn_b200.scripts.processing.InputGenerator",
+    "scripts.CNN.Evaluating": "f2cnn_b200.scripts.CNN.Evaluating",
 }
 
 # names that reference modules bind with `from X import name`
 _REBIND = {
-    "scripts.CNN.Evaluating": {
-        "ExtractEnvelopeFromMatrix": ("scripts.processing.EnvelopeExtraction", "ExtractEnvelopeFromMatrix"),
-        "GetArrayFromWAV": ("scripts.processing.GammatoneFiltering", "GetArrayFromWAV"),
-        "GetFilteredOutputFromArray": ("scripts.processing.GammatoneFiltering", "GetFilteredOutputFromArray"),
-        "filters": ("gammatone", "filters"),
-    },
     "scripts.plotting.PlottingProcessing": {
         "ExtractEnvelopeFromMatrix": ("scripts.processing.EnvelopeExtraction", "ExtractEnvelopeFromMatrix"),
         "GetArrayFromWAV": ("scripts.processing.GammatoneFiltering", "GetArrayFromWAV"),
@@ -45,6 +41,9 @@ _REBIND = {
         "FilterAllOrganisedFiles": ("scripts.processing.GammatoneFiltering", "FilterAllOrganisedFiles"),
         "ExtractAllEnvelopes": ("scripts.processing.EnvelopeExtraction", "ExtractAllEnvelopes"),
         "GenerateInputData": ("scripts.processing.InputGenerator", "GenerateInputData"),
+        "EvaluateOneWavFile": ("scripts.CNN.Evaluating", "EvaluateOneWavFile"),
+        "EvaluateRandom": ("scripts.CNN.Evaluating", "EvaluateRandom"),
+        "EvaluateWithNoise": ("scripts.CNN.Evaluating", "EvaluateWithNoise"),
     },
 }
 
@@ -55,7 +54,8 @@ def _ensure_parent_packages():
     """`scripts` and `scripts.processing` come from the reference tree when it is importable
     (so that LabelDataGenerator, CNN, plotting ... keep resolving); otherwise this package's
     own `scripts` packages stand in, so that the hot-path modules import on their own."""
-    for ref_pkg, ours in (("scripts", "f2cnn_b200.scripts"), ("scripts.processing", "f2cnn_b200.scripts.processing")):
+    for ref_pkg, ours in (("scripts", "f2cnn_b200.scripts"), ("scripts.processing", "f2cnn_b200.scripts.processing"),
+                          ("scripts.CNN", "f2cnn_b200.scripts.CNN")):
         if ref_pkg in sys.modules:
             continue
         try:
@@ -93,7 +93,7 @@ def install():
 
 def uninstall():
     """Restore whatever install() displaced (used by tests)."""
-    for ref_name in list(_MODULES) + ["scripts.processing", "scripts"]:
+    for ref_name in list(_MODULES) + ["scripts.CNN", "scripts.processing", "scripts"]:
         prev = _installed.pop(ref_name, None)
         if prev is not None:
             sys.modules[ref_name] = prev

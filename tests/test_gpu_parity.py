@@ -266,3 +266,29 @@ def test_error_behaviour(gpu):
         engine.Plan(bad)
     with pytest.raises(ValueError):
         api.dense_frames(np.zeros(4000, dtype=np.int16), co, True, 50, normalize=True)  # all-zero frames: min <= 0
+
+
+def test_evalnoise_config5_frames_and_cnn_forward(gpu, oracle):
+    """configs[4]: noise-mixed float64 utterance at 0/10/20 dB SNR -> filterbank -> envelope ->
+    dense framing -> normalizeInput -> CNN forward (seeded weights; there is no Keras oracle,
+    so the forward pass is checked for consistency between GPU-made and oracle-made frames)."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import cnn, synth
+    co = coefs128()
+    base = synth.speech_like_i16(8000, seed=31)
+    rng = np.random.default_rng(3)
+    model = cnn.seeded_model(0)
+    for snr_db in (0, 10, 20):
+        rms = np.sqrt(np.mean(base.astype(np.float64) ** 2))
+        wave = base + rng.normal(scale=rms / 10 ** (snr_db / 20.0), size=base.shape[0])
+        frames = api.dense_frames(wave, co, True, 50, normalize=True)
+        nb = base.shape[0] - 11 * 160
+        assert frames.shape == (nb, 11, 128) and frames.dtype == np.float64
+        _, eo, _ = oracle.utterance(wave, co, True, 50)
+        pick = [0, 1, 777, nb - 1]
+        want = np.stack([oracle.normalize_input(oracle.dense_frames(eo, 5, 160, i, i + 1)[0]) for i in pick])
+        assert np.max(np.abs(frames[pick] - want)) <= 5e-4  # log-min-max domain, values in [0, 1]
+        s_gpu = cnn.predict(model, torch.from_numpy(frames[pick]).cuda().float()).cpu().numpy()
+        s_ref = cnn.predict(model, torch.from_numpy(want).cuda().float()).cpu().numpy()
+        assert s_gpu.shape == (4, 2) and np.allclose(s_gpu.sum(axis=1), 1.0, atol=1e-5)
+        assert np.max(np.abs(s_gpu - s_ref)) <= 2e-3

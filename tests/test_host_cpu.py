@@ -137,6 +137,30 @@ def test_dropin_install_registers_reference_module_paths():
             assert callable(getattr(EnvelopeExtraction, name))
         for name in ("GetListOfEnvelopeFilesAndTimepoints", "GenerateInputData"):
             assert callable(getattr(InputGenerator, name))
-        assert len(mods) == 5
+        assert len(mods) == 6
+        from scripts.CNN import Evaluating
+        for name in ("EvaluateOneWavArray", "EvaluateOneWavFile", "EvaluateRandom", "EvaluateWithNoise", "RMS",
+                     "SNRdbToSNRlinear"):
+            assert callable(getattr(Evaluating, name))
     finally:
         dropin.uninstall()
+
+
+def test_normalize_input_bit_exact_vs_reference_golden():
+    from f2cnn_b200.scripts.CNN.Training import normalizeInput
+    g = load_golden("c256_f64.npz")
+    for j in range(len(g["frames_i"])):
+        assert np.array_equal(normalizeInput(g["frames"][j].copy()), g["frames_norm"][j])
+    flat = np.full((11, 4), 3.0)
+    assert normalizeInput(flat) is flat and np.all(flat == 0)  # constant frame: zero-filled in place
+    with pytest.raises(ValueError):
+        normalizeInput(np.array([[1.0, -1.0]]))
+
+
+def test_rms_keeps_the_int16_overflow_quirk():
+    from f2cnn_b200.scripts.CNN.Evaluating import RMS, SNRdbToSNRlinear
+    x = np.array([1000, -2000, 30000], dtype=np.int16)
+    with np.errstate(over="ignore"):
+        assert RMS(x) == np.sqrt(np.mean(np.square(x)))          # squares wrap in int16 like the reference
+    assert RMS(x) != pytest.approx(np.sqrt(np.mean(x.astype(np.float64) ** 2)))
+    assert SNRdbToSNRlinear(10) == 10.0
