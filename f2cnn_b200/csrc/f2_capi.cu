@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/f2cnn_b200.h"
+#include "f2_edge.cuh"
 #include "f2_fused.cuh"
 #include "f2_lanes.cuh"
 #include "f2_post.cuh"
@@ -82,6 +83,7 @@ struct f2_plan {
     int C = 0;
     int c_pad = 0;
     float* d_chan = nullptr;
+    float* d_scan_mats = nullptr;  // [C][kScanLevels][8][8] block transition powers for the edge scan
     std::vector<float> h_chan;  // host copy of the parameter block (for the __constant__ upload)
     long long id = 0;
     int w_imag = 0, w_edge = 0, w_casc = 0;
@@ -103,6 +105,7 @@ struct f2_batch {
     std::vector<f2::UttDesc> utts;
     std::vector<long long> frame_off;
     long long n_items = 0;
+    long long n_whole = 0;  // items if no utterance were split in time
     f2::UttDesc* d_utts = nullptr;
     f2::Item* d_items = nullptr;
     long long total_samples = 0, total_frames = 0, total_ring = 0;
@@ -175,12 +178,18 @@ int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** ou
     p->w_imag = round_up_tile(21.5 / min_nlr);
     p->w_edge = round_up_tile(29.0 / min_nlr);
     p->w_casc = p->w_edge;
+    std::vector<float> mats((size_t)C * f2::kScanLevels * 64);
+    for (int c = 0; c < C; ++c) f2::build_scan_matrices(par.data(), c_pad, c, mats.data() + (size_t)c * f2::kScanLevels * 64);
     cudaError_t e = cudaMalloc(&p->d_chan, par.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_chan, par.data(), par.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_scan_mats, mats.size() * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(p->d_scan_mats, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = f2::init_twiddles(0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (p->d_chan) cudaFree(p->d_chan);
+        if (p->d_scan_mats) cudaFree(p->d_scan_mats);
         delete p;
         return fail(F2_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
     }
@@ -192,6 +201,7 @@ int f2_plan_destroy(f2_plan* plan) {
     if (!plan) return F2_OK;
     DeviceGuard guard(plan->device);
     if (plan->d_chan) cudaFree(plan->d_chan);
+    if (plan->d_scan_mats) cudaFree(plan->d_scan_mats);
     delete plan;
     return F2_OK;
 }
@@ -294,6 +304,7 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         return (a.t1 - a.t0) > (c.t1 - c.t0);
     });
     b->n_items = (long long)items.size();
+    b->n_whole = whole;
 
     // ---- lane streams: (utterance, time chunk), 32 per CTA, kLaneWarps channels per CTA ------
     {
@@ -539,6 +550,20 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     fp.gfb_t = gfb_t;
     fp.env_t = env_t;
     fp.dec = a->dec;
+    fp.edge = nullptr;
+    if (need_env && b->n_items > b->n_whole) {
+        // time-chunked batch: the edge residuals are per utterance, compute them once instead of
+        // in every chunk.  Few (utterance, channel) pairs -> chunked scan (low latency), many ->
+        // one sequential thread per channel.
+        const long long scan_ctas = (long long)b->n_utts * ((plan->C + 3) / 4);
+        if (plan->w_edge <= f2::kScanWindow && scan_ctas <= 148 * 16)
+            F2_CUDA(f2::launch_edge_scan(b->d_utts, b->n_utts, plan->d_chan, plan->d_scan_mats, plan->C, plan->c_pad, xz,
+                                         edge, stream));
+        else
+            F2_CUDA(f2::launch_edge(b->d_utts, b->n_utts, plan->d_chan, plan->C, plan->c_pad, xz, plan->w_edge, edge,
+                                    stream));
+        fp.edge = edge;
+    }
     fp.C = plan->C;
     fp.c_pad = plan->c_pad;
     fp.step = b->step;

@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     const bool need_env = p.env_t != nullptr || p.dec != nullptr;
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
     const bool full_out = p.gfb_t != nullptr || p.env_t != nullptr;
-    const int nE = need_imag ? (n - tE0 + kTile - 1) / kTile : 0;
+    const bool edge_given = p.edge != nullptr;  // chunked batches: one edge pass per utterance, not per chunk
+    const int nE = (need_imag && !edge_given) ? (n - tE0 + kTile - 1) / kTile : 0;
     const int w_lpf = (p.lpf && need_env) ? p.w_lpf : 0;
     int ts, tenv;
     if (t0 - w_lpf - p.w_casc <= 0) {
@@ -286,6 +287,12 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     State s;
     reset(s);
     float ee[4] = {0.f, 0.f, 0.f, 0.f}, eo[4] = {0.f, 0.f, 0.f, 0.f};
+    if (edge_given && need_imag && active) {
+        const float4* e = reinterpret_cast<const float4*>(p.edge + ((size_t)item.utt * p.C + c) * 8);
+        const float4 v0 = __ldg(e), v1 = __ldg(e + 1);
+        ee[0] = v0.x; ee[1] = v0.y; ee[2] = v0.z; ee[3] = v0.w;
+        eo[0] = v1.x; eo[1] = v1.y; eo[2] = v1.z; eo[3] = v1.w;
+    }
     OutCtx o;
     o.C = (size_t)p.C;
     o.step = p.step;

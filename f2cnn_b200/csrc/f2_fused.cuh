@@ -13,6 +13,7 @@ struct FusedParams {
     float* gfb_t;        // full-rate filterbank output, time-major [t][C]   (nullable)
     float* env_t;        // full-rate envelope, time-major [t][C]            (nullable)
     float* dec;          // decimated envelope frames [frame][C]             (nullable)
+    const float* edge;   // precomputed edge residuals [utt][C][8] (f2_edge.cu); null: compute in-kernel
     int C;
     int c_pad;
     int step;            // decimation step: int(fs * SAMPLING_PERIOD / 1e6)   (InputGenerator.py:65)

@@ -50,80 +50,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- edge residuals ------------------------------------------------------------------------
-// One thread per channel, CTA = (utterance, 128 channels): real cascade over the last w_edge
-// samples from zero state (exact when the utterance is shorter), then
-//   e0 = b1*y[n-1] + b2*y[n-2] - z_k*u[n-1] = (cy-1)*y - cq*q - z_k*u,   e1 = b2*y[n-1] = cq*y
-// in the a0-free stage variables.  Stored parity-resolved: edge[0..3] multiplies G at even t,
-// edge[4..7] at odd t ((t-n) odd -> e0).
-__global__ void __launch_bounds__(kChanPerBlock) edge_kernel(const UttDesc* utts, const float* __restrict__ chan,
-                                                             int C, int c_pad, const float2* __restrict__ xz,
-                                                             int w_edge, float* __restrict__ edge) {
-    const UttDesc ut = utts[blockIdx.x];
-    const int c = blockIdx.y * kChanPerBlock + threadIdx.x;
-    if (c >= C || ut.n <= 0) return;
-    float z[4], cq[4], ncy[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        z[i] = chan[(P_Z + i) * c_pad + c];
-        cq[i] = chan[(P_CQ + i) * c_pad + c];
-        ncy[i] = chan[(P_NCY + i) * c_pad + c];
-    }
-    float y[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    float up0 = 0.f;
-    const int n = ut.n;
-    int t0 = n - w_edge;
-    t0 = t0 > 0 ? t0 : 0;
-    const float2* src = xz + ut.ring_off;
-    if (ut.N2 > 2) {
-#pragma unroll 4
-        for (int t = t0; t < n; ++t) {
-            float u = __ldg(&src[t].x);
-            float up = up0;
-            up0 = u;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float in = fmaf(z[i], up, u);
-                const float yo = y[i];
-                float qn = fmaf(cq[i], q[i], in);
-                qn = fmaf(ncy[i], yo, qn);
-                const float yn = yo + qn;
-                q[i] = qn;
-                y[i] = yn;
-                up = yo;
-                u = yn;
-            }
-        }
-    }
-    float e0[4], e1[4];
-    float uprev = up0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float cy = -ncy[i];
-        e0[i] = fmaf(cy - 1.0f, y[i], -cq[i] * q[i]) - z[i] * uprev;
-        e1[i] = cq[i] * y[i];
-        uprev = y[i];
-    }
-    if (ut.N2 <= 2) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) e0[i] = e1[i] = 0.f;
-    }
-    const bool n_odd = (n & 1) != 0;
-    float4* o = reinterpret_cast<float4*>(edge + ((size_t)blockIdx.x * C + c) * 8);
-    const float4 even = n_odd ? make_float4(e0[0], e0[1], e0[2], e0[3]) : make_float4(e1[0], e1[1], e1[2], e1[3]);
-    const float4 odd = n_odd ? make_float4(e1[0], e1[1], e1[2], e1[3]) : make_float4(e0[0], e0[1], e0[2], e0[3]);
-    o[0] = even;
-    o[1] = odd;
-}
-
-cudaError_t launch_edge(const UttDesc* utts, int n_utts, const float* chan, int C, int c_pad, const float2* xz,
-                        int w_edge, float* edge, cudaStream_t stream) {
-    if (n_utts <= 0) return cudaSuccess;
-    dim3 grid(n_utts, (C + kChanPerBlock - 1) / kChanPerBlock);
-    edge_kernel<<<grid, kChanPerBlock, 0, stream>>>(utts, chan, C, c_pad, xz, w_edge, edge);
-    return cudaGetLastError();
-}
-
 // ---- lane kernel ---------------------------------------------------------------------------
 struct CoefU {  // warp-uniform
     float z[4], cq[4], ncy[4], g4;

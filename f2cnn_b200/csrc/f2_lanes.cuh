@@ -2,6 +2,7 @@
 // hot path with warp-uniform coefficients (lane = stream, warp = channel).
 #pragma once
 #include "f2_common.cuh"
+#include "f2_edge.cuh"
 
 #ifndef F2_LANE_WARPS
 #define F2_LANE_WARPS 4
@@ -45,8 +46,6 @@ struct LaneParams {
 };
 
 cudaError_t upload_lane_constants(const float* host_par, int c_pad, cudaStream_t stream);
-cudaError_t launch_edge(const UttDesc* utts, int n_utts, const float* chan, int C, int c_pad, const float2* xz,
-                        int w_edge, float* edge, cudaStream_t stream);
 cudaError_t launch_lanes(const LaneParams& p, int n_groups, cudaStream_t stream);
 int lane_tile_samples();
 

@@ -292,3 +292,29 @@ def test_evalnoise_config5_frames_and_cnn_forward(gpu, oracle):
         s_ref = cnn.predict(model, torch.from_numpy(want).cuda().float()).cpu().numpy()
         assert s_gpu.shape == (4, 2) and np.allclose(s_gpu.sum(axis=1), 1.0, atol=1e-5)
         assert np.max(np.abs(s_gpu - s_ref)) <= 2e-3
+
+
+def test_chunked_batch_uses_per_utterance_edge_table(gpu, oracle):
+    """A batch that is split in time AND has many (utterance, channel) pairs takes the sequential
+    edge kernel (the single-utterance tests above take the chunked-scan edge kernel); both must
+    agree with the oracle and with the unsplit run."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = coefs128()
+    lens = [9000 + 37 * i for i in range(640)]
+    waves = [synth.white_noise_i16(n, seed=500 + i) for i, n in enumerate(lens)]
+    flat = torch.from_numpy(np.concatenate(waves)).cuda()
+    plan = engine.plan_for(co)
+    split = plan.batch(lens)                   # 640 utterances < target -> time chunks
+    whole = plan.batch(lens, target_items=1)   # one item per utterance, in-kernel edge pass
+    assert split.num_items > whole.num_items == 640
+    a = split.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
+    b = whole.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
+    for u in (0, 319, 639):
+        _, eo, _ = oracle.utterance(waves[u], co, True, 50)
+        f0, f1 = split.frame_offsets[u], split.frame_offsets[u + 1]
+        want = eo[:, ::160].T
+        scale = np.sqrt(np.mean(eo ** 2, axis=1))[None, :]
+        assert np.max(np.abs(a[f0:f1] - want) / scale) <= TOL
+        assert np.max(np.abs(b[f0:f1] - want) / scale) <= TOL
+        assert np.max(np.abs(a[f0:f1] - b[f0:f1]) / scale) <= 2e-5
