@@ -274,15 +274,25 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
 
     // ---- work items: (utterance, channel block, time chunk) -------------------------------
     const int cblocks = (plan->C + f2::kChanPerBlock - 1) / f2::kChanPerBlock;
-    if (target_items <= 0) target_items = 148 * 4 * 4;  // 4 resident CTAs per SM, 4 waves
+    // Time chunking policy.  Whole utterances when they already give ~1 wave of CTAs (4 resident
+    // CTAs on each of 148 SMs); otherwise chunks, preferably >= 16384 samples (each chunk pays
+    // w_casc (+ w_lpf) samples of warm-up) and a whole number of waves, never below 2048.
+    const long long wave_ctas = 148 * 4;
     long long whole = 0;
     for (int u = 0; u < n_utts; ++u) whole += lengths[u] > 0 ? cblocks : 0;
     long long seg = (long long)1 << 40;  // no splitting
-    if (whole < target_items && wave > 0) {
-        // split so that about target_items chunks exist, but never below 2048 samples
-        // (each chunk pays w_casc (+ w_lpf) samples of warm-up)
-        seg = (long long)align_up((size_t)std::max<long long>(wave * cblocks / target_items, 2048), f2::kTile);
+    if (target_items > 0) {
+        if (whole < target_items && wave > 0)
+            seg = (long long)align_up((size_t)std::max<long long>(wave * cblocks / target_items, 2048), f2::kTile);
+    } else if (whole < wave_ctas && wave > 0) {
+        long long best = std::max<long long>(wave * cblocks / wave_ctas, 2048);
+        for (int waves = 4; waves >= 2; --waves) {
+            const long long cand = wave * cblocks / (waves * wave_ctas);
+            if (cand >= 16384) { best = cand; break; }
+        }
+        seg = (long long)align_up((size_t)best, f2::kTile);
     }
+    if (target_items <= 0) target_items = 4 * wave_ctas;  // lane-stream decomposition below
     std::vector<f2::Item> items;
     for (int u = 0; u < n_utts; ++u) {
         const int n = b->utts[(size_t)u].n;

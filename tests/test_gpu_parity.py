@@ -311,7 +311,7 @@ def test_chunked_batch_uses_per_utterance_edge_table(gpu, oracle):
     waves = [synth.white_noise_i16(n, seed=500 + i) for i, n in enumerate(lens)]
     flat = torch.from_numpy(np.concatenate(waves)).cuda()
     plan = engine.plan_for(co)
-    split = plan.batch(lens)                   # 640 utterances < target -> time chunks
+    split = plan.batch(lens, target_items=4096)  # forced time chunks on a many-utterance batch
     whole = plan.batch(lens, target_items=1)   # one item per utterance, in-kernel edge pass
     assert split.num_items > whole.num_items == 640
     a = split.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()

@@ -1,0 +1,63 @@
+"""Device-side timings of the BASELINE.json configs that are not the bench.py headline:
+config 1 (single 3 s utterance, latency), config 4 (600 s stream, 256 channels, cut-off sweep),
+config 5 (evalnoise front end: dense framing + normalisation + CNN forward)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from f2cnn_b200 import api, cnn, engine, synth
+from f2cnn_b200.gammatone import filters
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = engine.DeviceEvent(), engine.DeviceEvent()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_ms(b) / reps
+
+out = {}
+co128 = filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, 100))
+co256 = filters.make_erb_filters(16000, filters.centre_freqs(16000, 256, 100))
+# ---- config 1 ----
+w = synth.white_noise_i16(48000, 0)
+plan = engine.plan_for(co128)
+wd = torch.from_numpy(w).cuda()
+for target, tag in ((1, "one_item"), (0, "default_chunks")):
+    b = plan.batch([48000], target_items=target)
+    dec = torch.empty((b.total_frames, 128), device="cuda")
+    ms = timed(lambda: b.run(wd, lpf=True, cutoff=50, out={"dec": dec}), reps=20)
+    out["config1_dec_%s" % tag] = {"items": b.num_items, "device_ms": ms, "channel_samples_per_s": 128 * 48000 / ms * 1e3}
+t = time.perf_counter(); centers = synth.label_grid(48000)
+for _ in range(5):
+    api.features_to_windows([w], co128, [centers], True, 50)
+out["config1_api_windows_host_ms"] = (time.perf_counter() - t) / 5 * 1e3
+t = time.perf_counter()
+for _ in range(3):
+    api.filterbank_envelope(w, co128, True, 50, with_gfb=True)
+out["config1_api_gfb_env_float64_host_ms"] = (time.perf_counter() - t) / 3 * 1e3
+# ---- config 4 ----
+n = 9_600_000
+w4 = torch.from_numpy(synth.white_noise_i16(n, seed=2)).cuda()
+plan4 = engine.plan_for(co256)
+b4 = plan4.batch([n])
+dec4 = torch.empty((b4.total_frames, 256), device="cuda")
+for cut in (20, 50, 100):
+    ms = timed(lambda: b4.run(w4, lpf=True, cutoff=cut, out={"dec": dec4}), reps=3, warm=1)
+    out["config4_cutoff%d" % cut] = {"items": b4.num_items, "device_ms": ms, "channel_samples_per_s": 256.0 * n / ms * 1e3}
+# ---- config 5 ----
+base = synth.speech_like_i16(48000, seed=31)
+wave = base + np.random.default_rng(3).normal(scale=300.0, size=48000)
+model = cnn.seeded_model(0)
+def eval_path():
+    b5 = plan.batch([48000])
+    res = b5.run(torch.from_numpy(wave).cuda(), lpf=True, cutoff=50, env_t=True)
+    frames, flag = engine.dense_frames(res["env_t"], 11, 160, 0, 48000 - 1760, normalize=True, out_dtype=torch.float32)
+    return cnn.predict(model, frames)
+ms = timed(eval_path, reps=5)
+out["config5_eval_frontend_plus_cnn"] = {"frames": 48000 - 1760, "device_ms": ms,
+                                         "note": "reference: 25 s Python framing + 0.9 s normalise per utterance before Keras"}
+print(json.dumps(out, indent=1))
