@@ -324,3 +324,26 @@ def test_chunked_batch_uses_per_utterance_edge_table(gpu, oracle):
         assert np.max(np.abs(a[f0:f1] - want) / scale) <= TOL
         assert np.max(np.abs(b[f0:f1] - want) / scale) <= TOL
         assert np.max(np.abs(a[f0:f1] - b[f0:f1]) / scale) <= 2e-5
+
+
+@pytest.mark.parametrize("fs,C,low,n,dtype", [(44100, 100, 20, 30000, np.float32), (8000, 37, 50, 12345, np.int16),
+                                               (16000, 300, 100, 5000, np.float64)])
+def test_other_filterbanks_and_dtypes(gpu, oracle, fs, C, low, n, dtype):
+    """Channel counts that are not multiples of 32 / 128, other sample rates (slower poles ->
+    longer warm-ups derived at plan creation), float32 / float64 waves, whole and chunked."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = filters.make_erb_filters(fs, filters.centre_freqs(fs, C, low))
+    w = synth.white_noise_i16(n, seed=n).astype(dtype)
+    go = oracle.erb_filterbank(w, co)
+    eo = oracle.extract_envelope(go, True, 50)
+    plan = engine.plan_for(co)
+    wd = torch.from_numpy(w).cuda()
+    for target in (1, 0, 64):
+        res = plan.batch([n], target_items=target).run(wd, lpf=True, cutoff=50, gfb=torch.float64, env=torch.float64,
+                                                       dec=True)
+        gfb = res["gfb"].cpu().numpy().reshape(C, n)
+        env = res["env"].cpu().numpy().reshape(C, n)
+        assert rel_err(gfb, go).max() <= TOL, (target, "gfb")
+        assert rel_err(env, eo).max() <= TOL, (target, "env")
+        assert np.array_equal(res["dec"].cpu().numpy(), env[:, ::160].astype(np.float32).T)
