@@ -250,7 +250,7 @@ def main():
             out_host = torch.empty((n_windows, dots, C), dtype=torch.float32)
 
         pipe = engine.WindowPipeline(plan, lengths, [np.arange(nwin[u], dtype=np.int64) for u in range(len(lengths))],
-                                     dots=dots, step=STEP, lpf=True, cutoff=CUTOFF, n_sub=12)
+                                     dots=dots, step=STEP, lpf=True, cutoff=CUTOFF, n_sub=24)
         assert pipe.n_windows == n_windows
 
         def e2e_step():
@@ -277,7 +277,7 @@ def main():
         e2e = {"value": world * cs_per_step / (ms_e2e / k * 1e-3), "unit": "channel-samples/s",
                "h2d_bytes_per_step": int(wave_host.numel() * 2), "d2h_bytes_per_step": int(out_host.numel() * 4),
                "ms_per_step": ms_e2e / k, "pinned_output": bool(out_host.is_pinned()),
-               "path": "engine.WindowPipeline: 12 sub-batches, H2D / compute / D2H on three streams"}
+               "path": "engine.WindowPipeline: 24 sub-batches, H2D / compute / D2H on three streams"}
         del out_host
 
     if rank != 0:
@@ -295,7 +295,10 @@ def main():
     fma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s, nominal FP32 FMA at max clock
     achieved = FLOP_PER_CS * cs_per_step / (fused_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32_fma", "kernel": "fused_kernel", "achieved": achieved, "peak": fma_peak,
-                "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / fma_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one fused_kernel launch on this workload,
+                # ncu --set full capture summarised in profiles/r01e_ncu_fused_v2.md (algorithmic: 3.37e9)
+                "traffic": 3.594e9 if args.utts == N_UTTS else None,
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 entry); "
                                "tools/fma_peak.cu measured 73.8 TFLOP/s sustained (FFMA2) on this pool",
                 "kernel_ms": fused_ms, "kernel_share_of_step": fused_ms / ms_step,

@@ -209,7 +209,10 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
     }
 }
 
-template <int MINB, int U>
+// EDGE: the edge residuals come from the per-utterance table (time-chunked batches) instead of
+// the in-kernel pass; a template parameter so that the whole-utterance instantiation keeps its
+// register allocation.
+template <int MINB, int U, bool EDGE>
 __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedParams p) {
     __shared__ __align__(128) float2 s_xz[kStages][kTile];
     __shared__ __align__(128) float s_g[kStages][kTile];
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     const bool need_env = p.env_t != nullptr || p.dec != nullptr;
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
     const bool full_out = p.gfb_t != nullptr || p.env_t != nullptr;
-    const bool edge_given = p.edge != nullptr;  // chunked batches: one edge pass per utterance, not per chunk
+    constexpr bool edge_given = EDGE;  // chunked batches: one edge pass per utterance, not per chunk
     const int nE = (need_imag && !edge_given) ? (n - tE0 + kTile - 1) / kTile : 0;
     const int w_lpf = (p.lpf && need_env) ? p.w_lpf : 0;
     int ts, tenv;
@@ -380,15 +383,14 @@ cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream)
         const char* v = getenv("F2_FUSED_VARIANT");
         variant = v ? atoi(v) : 0;
     }
+    if (p.edge) {
+        fused_kernel<4, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
     switch (variant) {
-        case 58: fused_kernel<5, 8><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 68: fused_kernel<6, 8><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 44: fused_kernel<4, 4><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 54: fused_kernel<5, 4><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 64: fused_kernel<6, 4><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 416: fused_kernel<4, 16><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 316: fused_kernel<3, 16><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        default: fused_kernel<4, 8><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 58: fused_kernel<5, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 416: fused_kernel<4, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        default: fused_kernel<4, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
     }
     return cudaGetLastError();
 }

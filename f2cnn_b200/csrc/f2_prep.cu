@@ -20,6 +20,8 @@
 
 #include <math.h>
 
+#include <algorithm>
+
 namespace f2 {
 
 constexpr int kFftThreads = 256;
@@ -140,6 +142,9 @@ __device__ __forceinline__ void smem_fft(float2* s, int pitch, int logL, int bat
     }
 }
 
+// legs of 128 / 256 points have a register-pass implementation (see the fast kernels below)
+__host__ __device__ inline bool fast_leg(int l) { return l == 7 || l == 8; }
+
 __device__ __forceinline__ int bitrev(int v, int bits) { return bits ? (int)(__brev((unsigned)v) >> (32 - bits)) : 0; }
 
 __host__ __device__ inline void fft_split(int log2M, int& l1, int& l2) {
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(PrepParams p, flo
     if (log2M <= kTwLog) return;  // single-pass sizes skip the column pass
     int l1, l2;
     fft_split(log2M, l1, l2);
+    if (fast_leg(l1) && fast_leg(l2)) return;  // taken by fft_cols_fast_kernel
     const int M1 = 1 << l1, M2 = 1 << l2;
     int B = kFftSmemPts >> l1;
     if (B > M2) B = M2;
@@ -203,6 +209,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(PrepParams p, con
     fft_split(log2M, l1, l2);
     if (SRC_WAVE && l1 != 0) return;   // two-pass sizes were packed by the column pass
     if (!SRC_WAVE && !INV && l1 == 0) return;  // forward single-pass sizes take the SRC_WAVE launch
+    if (l1 != 0 && fast_leg(l1) && fast_leg(l2)) return;  // taken by fft_rows_fast_kernel
     const int M1 = 1 << l1, M2 = 1 << l2;
     int B = kFftSmemPts >> l2;
     if (B > M1) B = M1;
@@ -235,6 +242,212 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(PrepParams p, con
             zout[(size_t)k2 * M1 + r0 + b] = s_fft[b * pitch + sw(k2)];
         }
     }
+}
+
+// =============================================================================================
+// Fast legs for the sizes real utterances use (legs of 128 and 256 points: N2 = 32768 ... 131072).
+// Each leg is two register passes -- L = R1 x R2 with R1 = 16, R2 = L/16 -- around ONE
+// shared-memory exchange, instead of log4(L) shared-memory passes:
+//   pass 1: thread (fft b, n2) loads x[n1*R2 + n2], n1 < 16, runs a 16-point FFT in registers,
+//           multiplies by w_L^(n2*k1) and writes A[b][k1][n2];
+//   pass 2: thread (fft b, k1) reads A[b][k1][n2], n2 < R2, runs an R2-point FFT in registers:
+//           X[k1 + 16*k2].
+// =============================================================================================
+template <bool INV>
+__device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+    const float2 j13 = INV ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);  // -/+ i * d13
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = cadd(d02, j13);
+    a3 = csub(d02, j13);
+}
+
+template <bool INV>
+__device__ __forceinline__ float2 cmul_w16(float2 v, int m) {  // v * w_16^m, m = 0..9 (compile-time after unrolling)
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+    float c, s;  // w_16^m = cos(2 pi m/16) - i sin(2 pi m/16)
+    switch (m) {
+        case 0: return v;
+        case 1: c = C1; s = S1; break;
+        case 2: c = R2; s = R2; break;
+        case 3: c = S1; s = C1; break;
+        case 4: c = 0.f; s = 1.f; break;
+        case 6: c = -R2; s = R2; break;
+        default: c = -C1; s = -S1; break;  // m = 9
+    }
+    const float2 w = make_float2(c, INV ? s : -s);
+    return cmul(v, w);
+}
+
+// 16-point FFT in registers; result for frequency k = (r >> 2) + 4 * (r & 3) is left in v[r].
+template <bool INV>
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) fft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1)
+#pragma unroll
+        for (int n2 = 1; n2 < 4; ++n2) v[4 * k1 + n2] = cmul_w16<INV>(v[4 * k1 + n2], n2 * k1);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) fft4<INV>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+__device__ __forceinline__ constexpr int out16(int r) { return (r >> 2) + 4 * (r & 3); }
+
+// 8-point FFT in registers; result for frequency k = (r >> 1) + 4 * (r & 1) is left in v[r].
+template <bool INV>
+__device__ __forceinline__ void fft8(float2 (&v)[8]) {
+    fft4<INV>(v[0], v[2], v[4], v[6]);
+    fft4<INV>(v[1], v[3], v[5], v[7]);
+    v[3] = cmul_w16<INV>(v[3], 2);  // w_8^1
+    v[5] = cmul_w16<INV>(v[5], 4);  // w_8^2
+    v[7] = cmul_w16<INV>(v[7], 6);  // w_8^3
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 a = v[2 * j], b = v[2 * j + 1];
+        v[2 * j] = cadd(a, b);
+        v[2 * j + 1] = csub(a, b);
+    }
+}
+__device__ __forceinline__ constexpr int out8(int r) { return (r >> 1) + 4 * (r & 1); }
+
+template <bool INV>
+__device__ __forceinline__ float2 leg_twiddle(int m, int logL) {  // w_L^m for 0 <= m < L
+    int idx = m << (kTwLog - logL);
+    float2 w;
+    if (idx >= (1 << (kTwLog - 1))) {
+        w = g_twiddle[idx - (1 << (kTwLog - 1))];
+        w = make_float2(-w.x, -w.y);
+    } else {
+        w = g_twiddle[idx];
+    }
+    if (INV) w.y = -w.y;
+    return w;
+}
+
+constexpr int kFastPts = 4096;  // complex points per CTA in the fast kernels
+
+// Shared layout A[b][k1][n2]: b * PB + k1 * (R2 + 1) + n2, PB odd.
+template <int LOGL>
+struct LegShape {
+    static constexpr int L = 1 << LOGL;
+    static constexpr int R2 = L / 16;
+    static constexpr int B = kFastPts / L;
+    static constexpr int P1 = R2 + 1;
+    static constexpr int PB = 16 * P1 + (((16 * P1) & 1) ? 0 : 1);
+};
+
+// Both passes of one leg for the B transforms of a CTA.  LOAD(b, n) -> float2 input element n
+// of transform b; STORE(b, k, value) consumes output frequency k.  256 threads.
+template <bool INV, int LOGL, typename LoadF, typename StoreF>
+__device__ __forceinline__ void leg_fft(float2* sA, bool b_fastest, LoadF load, StoreF store) {
+    using S = LegShape<LOGL>;
+    const int tid = threadIdx.x;
+    {   // pass 1: S::B * S::R2 == 256 threads
+        const int b = b_fastest ? tid % S::B : tid / S::R2;
+        const int n2 = b_fastest ? tid / S::B : tid % S::R2;
+        float2 v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = load(b, n1 * S::R2 + n2);
+        fft16<INV>(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int k1 = out16(r);
+            sA[b * S::PB + k1 * S::P1 + n2] = cmul(v[r], leg_twiddle<INV>(n2 * k1, LOGL));
+        }
+    }
+    __syncthreads();
+    // pass 2: S::B * 16 threads of work (256 for L = 256, 512 for L = 128)
+#pragma unroll 1
+    for (int t2 = tid; t2 < S::B * 16; t2 += kFftThreads) {
+        const int b = t2 % S::B, k1 = t2 / S::B;
+        const float2* a = sA + b * S::PB + k1 * S::P1;
+        if (S::R2 == 16) {
+            float2 v[16];
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) v[n2] = a[n2];
+            fft16<INV>(v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) store(b, k1 + 16 * out16(r), v[r]);
+        } else {
+            float2 v[8];
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) v[n2] = a[n2];
+            fft8<INV>(v);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) store(b, k1 + 16 * out8(r), v[r]);
+        }
+    }
+}
+
+template <bool INV, bool SRC_WAVE, int LOGL>
+__device__ __forceinline__ void cols_fast_body(const PrepParams& p, const UttDesc& ut, float* buf, float2* sA, int l2) {
+    using S = LegShape<LOGL>;
+    const int M2 = 1 << l2;
+    const int c0 = blockIdx.y * S::B;
+    if (c0 >= M2) return;
+    float2* z = reinterpret_cast<float2*>(buf + ut.ring_off);
+    const float sgn = INV ? 2.0f : -2.0f;
+    const float invM = 1.0f / (float)(1 << (LOGL + l2));
+    leg_fft<INV, LOGL>(
+        sA, true,
+        [&](int b, int n) {
+            const int e = n * M2 + c0 + b;
+            return SRC_WAVE ? load_pair(p.wave, p.wave_dtype, ut.wave_off, e, ut.n) : z[e];
+        },
+        [&](int b, int k, float2 v) {
+            const int n2 = c0 + b;
+            float sn, cs;
+            sincospif(sgn * (float)(n2 * k) * invM, &sn, &cs);
+            z[(size_t)k * M2 + n2] = cmul(v, make_float2(cs, sn));
+        });
+}
+
+template <bool INV, bool SRC_WAVE>
+__global__ void __launch_bounds__(kFftThreads) fft_cols_fast_kernel(PrepParams p, float* buf) {
+    __shared__ float2 sA[kFastPts + kFastPts / 8 + 64];
+    const UttDesc ut = p.utts[blockIdx.x];
+    const int log2M = ut.log2N2 - 1;
+    int l1, l2;
+    fft_split(log2M, l1, l2);
+    if (log2M <= kTwLog || !fast_leg(l1) || !fast_leg(l2)) return;
+    if (l1 == 7) cols_fast_body<INV, SRC_WAVE, 7>(p, ut, buf, sA, l2);
+    else cols_fast_body<INV, SRC_WAVE, 8>(p, ut, buf, sA, l2);
+}
+
+template <bool INV, bool DST_RING, int LOGL>
+__device__ __forceinline__ void rows_fast_body(const PrepParams& p, const UttDesc& ut, const float* in_buf,
+                                               float* out_buf, float2* sA, int l1) {
+    using S = LegShape<LOGL>;
+    const int M1 = 1 << l1;
+    const int r0 = blockIdx.y * S::B;
+    if (r0 >= M1) return;
+    const float2* zin = reinterpret_cast<const float2*>(in_buf + ut.ring_off);
+    float2* zout = DST_RING ? nullptr : reinterpret_cast<float2*>(out_buf + ut.ring_off);
+    float4* ring = DST_RING ? reinterpret_cast<float4*>(p.xz + ut.ring_off) : nullptr;
+    leg_fft<INV, LOGL>(
+        sA, false, [&](int b, int n) { return zin[(size_t)(r0 + b) * S::L + n]; },
+        [&](int b, int k, float2 v) {
+            const int m = k * M1 + r0 + b;
+            if (DST_RING) {
+                const float2 x = load_pair(p.wave, p.wave_dtype, ut.wave_off, m, ut.n);
+                ring[m] = make_float4(x.x, v.x, x.y, v.y);
+            } else {
+                zout[m] = v;
+            }
+        });
+}
+
+template <bool INV, bool DST_RING>
+__global__ void __launch_bounds__(kFftThreads) fft_rows_fast_kernel(PrepParams p, const float* in_buf, float* out_buf) {
+    __shared__ float2 sA[kFastPts + kFastPts / 8 + 64];
+    const UttDesc ut = p.utts[blockIdx.x];
+    const int log2M = ut.log2N2 - 1;
+    int l1, l2;
+    fft_split(log2M, l1, l2);
+    if (log2M <= kTwLog || !fast_leg(l1) || !fast_leg(l2)) return;
+    if (l2 == 7) rows_fast_body<INV, DST_RING, 7>(p, ut, in_buf, out_buf, sA, l1);
+    else rows_fast_body<INV, DST_RING, 8>(p, ut, in_buf, out_buf, sA, l1);
 }
 
 // ---- untangle the packed real FFT, apply the Hilbert multiplier, tangle for the inverse ----
@@ -363,19 +576,38 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
     }
     const bool two = (h.max_log2N2 - 1) > kTwLog;
     const bool one = h.min_log2N2 - 1 <= kTwLog;  // some utterances take the single-pass path
+    // sizes with 128/256-point legs (N2 = 2^15 .. 2^17) take the register-pass kernels
+    bool fast = false, slow2 = false;
+    int fast_blocks = 1;
+    for (int lg = h.min_log2N2; lg <= h.max_log2N2; ++lg) {
+        if (lg - 1 <= kTwLog) continue;
+        int l1, l2;
+        fft_split(lg - 1, l1, l2);
+        if (fast_leg(l1) && fast_leg(l2)) {
+            fast = true;
+            fast_blocks = std::max(fast_blocks, std::max((1 << l2) / (kFastPts >> l1), (1 << l1) / (kFastPts >> l2)));
+        } else {
+            slow2 = true;
+        }
+    }
+    const dim3 g_fast(h.n_utts, fast_blocks);
     const dim3 g_cols(h.n_utts, max_blocks(h, true));
     const dim3 g_rows(h.n_utts, max_blocks(h, false));
     float* A = p.bufA;
     float* B = p.bufB;
     // forward
-    if (two) fft_cols_kernel<false, true><<<g_cols, kFftThreads, smem, stream>>>(p, A);
-    if (two) fft_rows_kernel<false, false, false><<<g_rows, kFftThreads, smem, stream>>>(p, A, B);
+    if (fast) fft_cols_fast_kernel<false, true><<<g_fast, kFftThreads, 0, stream>>>(p, A);
+    if (fast) fft_rows_fast_kernel<false, false><<<g_fast, kFftThreads, 0, stream>>>(p, A, B);
+    if (two && slow2) fft_cols_kernel<false, true><<<g_cols, kFftThreads, smem, stream>>>(p, A);
+    if (two && slow2) fft_rows_kernel<false, false, false><<<g_rows, kFftThreads, smem, stream>>>(p, A, B);
     if (one) fft_rows_kernel<false, true, false><<<g_rows, kFftThreads, smem, stream>>>(p, nullptr, B);
     // Hilbert multiplier in place on B; the injection kernel goes to A (free from here on)
     hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, B, p.G);
     // inverse, last pass writes the (x, xi) ring
-    if (two) fft_cols_kernel<true, false><<<g_cols, kFftThreads, smem, stream>>>(p, B);
-    fft_rows_kernel<true, false, true><<<g_rows, kFftThreads, smem, stream>>>(p, B, nullptr);
+    if (fast) fft_cols_fast_kernel<true, false><<<g_fast, kFftThreads, 0, stream>>>(p, B);
+    if (fast) fft_rows_fast_kernel<true, true><<<g_fast, kFftThreads, 0, stream>>>(p, B, nullptr);
+    if (two && slow2) fft_cols_kernel<true, false><<<g_cols, kFftThreads, smem, stream>>>(p, B);
+    if (one || slow2) fft_rows_kernel<true, false, true><<<g_rows, kFftThreads, smem, stream>>>(p, B, nullptr);
     if (h.min_log2N2 < 2) plain_ring_kernel<<<g_ew, 256, 0, stream>>>(p, 1);
     return cudaGetLastError();
 }
