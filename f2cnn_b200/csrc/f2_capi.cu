@@ -500,7 +500,7 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     // Experimental (off by default, F2_USE_LANES=1): measured equal to the thread-per-channel
     // kernel (47.6 vs 47.0 ms on config 2) because ptxas keeps only a third of the coefficients
     // on the uniform datapath and the per-warp code copies press on the instruction cache.
-    static const bool use_lanes = getenv("F2_USE_LANES") != nullptr;
+    const bool use_lanes = getenv("F2_USE_LANES") != nullptr;
     if (b->lanes_ok && use_lanes && a->dec && !a->gfb && !a->env && !a->env_t) {
         static long long const_owner[64] = {0};
         const int dev = plan->device;
