@@ -1,0 +1,101 @@
+"""The reference-named modules end to end on the GPU: file drivers (`prepare filter`,
+`prepare envelope`, `prepare input`) in a temporary tree, and the small array functions."""
+import csv
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+CONF = ("[FILTERBANK]\nFRAMERATE=16000\nNCHANNELS=32\nLOW_FREQ=100\n"
+        "[CNN]\nFORMANT=2\nCENTERED=True\nRADIUS=5\nBATCH_SIZE=32\nEPOCHS=20\nRISK=0.05\nSAMPLING_PERIOD=10000\n")
+
+
+def rel(got, want):
+    r = np.sqrt(np.mean(want ** 2, axis=-1))
+    return (np.max(np.abs(got - want), axis=-1) / np.maximum(r, 1e-300)).max()
+
+
+@pytest.fixture()
+def tree(tmp_path, monkeypatch):
+    from scipy.io import wavfile
+    from f2cnn_b200 import synth
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "configF2CNN.conf").write_text(CONF)
+    waves = {}
+    for tt, name, n in (("TRAIN", "DR1.SPK0.SA1", 9000), ("TRAIN", "DR2.SPK1.SX7", 12000), ("TEST", "DR1.SPK2.SI3", 7000)):
+        d = tmp_path / "resources" / "f2cnn" / tt
+        d.mkdir(parents=True, exist_ok=True)
+        w = synth.speech_like_i16(n, seed=n)
+        wavfile.write(str(d / (name + ".WAV")), 16000, w)
+        waves[(tt, name)] = w
+    return tmp_path, waves
+
+
+def test_prepare_filter_envelope_input_drivers(tree, oracle):
+    tmp_path, waves = tree
+    import torch
+    assert torch.cuda.is_available()
+    from f2cnn_b200 import dropin, synth
+    dropin.install()
+    try:
+        from gammatone import filters
+        from scripts.processing import EnvelopeExtraction, GammatoneFiltering, InputGenerator
+        co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 32, 100))
+        GammatoneFiltering.FilterAllOrganisedFiles()
+        EnvelopeExtraction.ExtractAllEnvelopes(True, 50)
+        rows, want_rows = [], {}
+        for (tt, name), w in sorted(waves.items()):
+            base = tmp_path / "resources" / "f2cnn" / tt / name
+            gfb = np.load(str(base) + ".GFB.npy")
+            env = np.load(str(base) + ".ENV1.npy")
+            assert gfb.dtype == env.dtype == np.float64 and gfb.shape == env.shape == (32, len(w))
+            go, eo, _ = oracle.utterance(w, co, True, 50)
+            assert rel(gfb, go) <= TOL and rel(env, eo) <= TOL
+            assert np.array_equal(GammatoneFiltering.loadGFBMatrix(str(base) + ".GFB"), gfb)
+            dr, spk, sent = name.split(".")
+            tps = synth.label_grid(len(w))[::2]
+            for tp in tps:
+                rows.append([tt, dr, spk, sent, "aa", int(tp), 0.1, 0.01, 1])
+            want_rows[os.path.join(tt, name + ".ENV1.npy")] = oracle.gather_windows(env, tps)
+        os.makedirs("trainingData")
+        with open(os.path.join("trainingData", "label_data.csv"), "w") as f:
+            wr = csv.writer(f, lineterminator="\n")
+            for r in rows[::-1]:  # reversed CSV: rows must come out by sorted file key, CSV order within a file
+                wr.writerow(r)
+        InputGenerator.GenerateInputData(LPF=True, CUTOFF=50)
+        out = np.load(os.path.join("trainingData", "input_data_LPF50.npy"))
+        assert out.dtype == np.float32 and np.array_equal(out, np.load(os.path.join("trainingData", "last_input_data.npy")))
+        want = np.concatenate([want_rows[k][::-1] for k in sorted(want_rows)])
+        assert out.shape == want.shape
+        assert np.array_equal(out, want)  # pure gather + float64->float32 cast of the saved envelopes: exact
+        # ENV1 file missing but WAV present: rows come from the fused kernel instead
+        os.remove(str(tmp_path / "resources" / "f2cnn" / "TEST" / "DR1.SPK2.SI3.ENV1.npy"))
+        InputGenerator.GenerateInputData(inputFile=os.path.join("trainingData", "fused.npy"), LPF=True, CUTOFF=50)
+        out2 = np.load(os.path.join("trainingData", "fused.npy"))
+        scale = np.sqrt(np.mean(want.astype(np.float64) ** 2, axis=(0, 1)))
+        assert out2.shape == want.shape and np.max(np.abs(out2 - want) / scale[None, None, :]) <= TOL
+    finally:
+        dropin.uninstall()
+
+
+def test_array_functions(oracle):
+    import torch
+    assert torch.cuda.is_available()
+    from f2cnn_b200 import synth
+    from f2cnn_b200.scripts.processing import EnvelopeExtraction as EE, GammatoneFiltering as GF
+    from f2cnn_b200.gammatone import filters
+    co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 16, 100))
+    w = synth.white_noise_i16(5000, seed=8)
+    gfb = GF.GetFilteredOutputFromArray(w, co)
+    assert rel(gfb, oracle.erb_filterbank(w, co)) <= TOL
+    row = gfb[7]
+    an = EE.paddedHilbert(row)
+    want = oracle.padded_hilbert(row)
+    assert an.dtype == np.complex128 and np.array_equal(an.real, row)
+    assert np.max(np.abs(an.imag - want.imag)) <= TOL * np.sqrt(np.mean(row ** 2))
+    lp = EE.lowPassFilter(np.abs(want), 50)
+    assert np.max(np.abs(lp - oracle.low_pass_filter(np.abs(want), 50))) <= TOL * np.sqrt(np.mean(np.abs(want) ** 2))
+    env = EE.ExtractEnvelopeFromMatrix(gfb)  # defaults: LPF=False
+    assert rel(env, oracle.extract_envelope(gfb, False)) <= TOL
