@@ -9,6 +9,7 @@ import torch
 from . import engine
 
 _WAVE_DTYPES = (np.int16, np.float32, np.float64)
+_PIPELINE_BYTES = 256 << 20  # window tensors above this size go through engine.WindowPipeline
 
 
 def _as_wave(wave):
@@ -163,6 +164,17 @@ def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=
     phase = int(allidx[0] % step)
     on_grid = bool(np.all(allidx % step == phase))
     flat = np.concatenate(waves) if len(waves) > 1 else waves[0]
+    strided = on_grid and all(bool(np.all(np.diff(i, axis=1) == step)) for i in idx if i.size)
+    if strided and not device_out and total * dots * C * 4 >= _PIPELINE_BYTES and len(waves) >= 8:
+        # corpus-sized request: overlap H2D / compute / D2H over sub-batches (PCIe-bound path)
+        bases = [(i[:, 0] - phase) // step if i.size else np.zeros(0, dtype=np.int64) for i in idx]
+        pipe = engine.WindowPipeline(plan, lengths, bases, dots=dots, step=step, phase=phase, lpf=LPF, cutoff=CUTOFF,
+                                     n_sub=max(2, min(24, len(waves) // 64)))
+        wave_host = torch.from_numpy(flat).pin_memory()
+        out_host = torch.empty((total, dots, C), dtype=torch.float32, pin_memory=True)
+        pipe.run(wave_host, out_host)
+        torch.cuda.current_stream().synchronize()
+        return out_host.numpy()
     wave_dev = _to_device(flat, plan.device)
     if on_grid:
         batch = plan.batch(lengths, step=step, phase=phase)

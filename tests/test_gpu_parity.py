@@ -372,3 +372,42 @@ def test_experimental_lane_stream_kernel(gpu, oracle, monkeypatch):
             tol = TOL if n >= 255 else 2e-3
             assert np.max(np.abs(got[f0:f1] - eo[:, ::160].T) / scale) <= tol, (target, u)
             assert np.max(np.abs(got[f0:f1] - ref[f0:f1]) / scale) <= max(5e-5, tol / 2), (target, u)
+
+
+def test_corpus_sized_request_takes_the_pipelined_path(gpu, monkeypatch):
+    """features_to_windows on many utterances: the sub-batched, three-stream pipeline returns
+    exactly what the single-launch path returns."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = coefs128()
+    lengths = synth.corpus_lengths(96, lo=8000, hi=16000, seed=4)
+    waves = [synth.white_noise_i16(int(n), seed=900 + i) for i, n in enumerate(lengths)]
+    tps = [synth.label_grid(int(n)) for n in lengths]
+    a = api.features_to_windows(waves, co, tps, True, 50)
+    monkeypatch.setattr(api, "_PIPELINE_BYTES", 1)
+    b = api.features_to_windows(waves, co, tps, True, 50)
+    assert a.shape == b.shape == (sum(len(t) for t in tps), 11, 128)
+    # sub-batches run whole utterances (no time chunks) while the single launch of a 96-utterance
+    # batch splits them: same values to float32 noise, not bit for bit
+    scale = np.sqrt(np.mean(a.astype(np.float64) ** 2, axis=(0, 1)))
+    assert np.max(np.abs(a - b) / scale[None, None, :]) <= 5e-5
+
+
+def test_long_stream_config4_full_length(gpu, oracle):
+    """configs[3] at its full size on the GPU: 600 s (9.6 M samples, N2 = 2^24), 256 channels,
+    cut-off 20 Hz (the slowest low-pass pole); the float64 oracle checks four channels."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = load_golden("coefs.npz")["coefs_fs16000_c256_l100"]
+    n = 9_600_000
+    w = synth.white_noise_i16(n, seed=2)
+    sub = np.array([0, 85, 170, 255])
+    eo = oracle.extract_envelope(oracle.erb_filterbank(w, co[sub]), True, 20)
+    plan = engine.plan_for(co)
+    batch = plan.batch([n])
+    assert batch.num_items >= 148
+    dec = batch.run(torch.from_numpy(w).cuda(), lpf=True, cutoff=20, dec=True)["dec"].cpu().numpy()
+    assert dec.shape == (60000, 256)
+    want = eo[:, ::160].T
+    scale = np.sqrt(np.mean(eo ** 2, axis=1))[None, :]
+    assert np.max(np.abs(dec[:, sub] - want) / scale) <= TOL
