@@ -309,12 +309,14 @@ int lane_tile_samples() { return kLaneTile; }
 
 cudaError_t launch_lanes(const LaneParams& p, int n_groups, cudaStream_t stream) {
     if (n_groups <= 0) return cudaSuccess;
-    static bool attr_done = false;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
     const int smem = kLaneStages * kStageBytes;
-    if (!attr_done) {
+    if (dev >= 64 || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev < 64) attr_done[dev] = true;
     }
     dim3 grid((p.C + kLaneWarps - 1) / kLaneWarps, n_groups);  // x: the channel blocks of one group run together (L2)
     lane_kernel<<<grid, (kLaneWarps + 1) * 32, smem, stream>>>(p);

@@ -555,15 +555,18 @@ static int max_blocks(const HostPrepInfo& h, bool cols) {
 cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t stream) {
     if (h.n_utts <= 0) return cudaSuccess;
     if (h.max_log2N2 - 1 > 2 * kTwLog) return cudaErrorInvalidValue;
-    static bool attr_done = false;
+    // per device: the attribute belongs to the current device's copy of the function
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
     const int smem = (kFftSmemPts + kFftSmemPts / 16 + 512) * (int)sizeof(float2);
-    if (!attr_done) {
+    if (dev >= 64 || !attr_done[dev]) {
         cudaFuncSetAttribute(fft_cols_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_cols_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_rows_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_rows_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_rows_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_done = true;
+        if (dev < 64) attr_done[dev] = true;
     }
     const int maxN2 = 1 << h.max_log2N2;
     int ew_blocks = (maxN2 / 2 + 1023) / 1024;

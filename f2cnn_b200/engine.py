@@ -320,6 +320,43 @@ class WindowPipeline:
         return out_host
 
 
+class MultiGpuWindowPipeline:
+    """WindowPipeline over several GPUs of one box from ONE process: the utterances are cut into
+    contiguous ranges of about equal sample count, one per device; every device runs its own
+    WindowPipeline into its slice of the shared host output.  Utterances are independent, so
+    there is no collective -- the "gather" is each device's D2H copy landing at its row offset
+    (SURVEY.md section 8e).  All launches are asynchronous; one host thread drives all devices."""
+
+    def __init__(self, coefs, lengths, bases, devices=None, **kw):
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        U = int(lengths.shape[0])
+        devices = list(devices)[:max(1, min(len(devices), U))]
+        cum = np.concatenate([[0], np.cumsum(lengths)])
+        cuts = [int(np.searchsorted(cum, cum[-1] * k / len(devices))) for k in range(len(devices) + 1)]
+        cuts[0], cuts[-1] = 0, U
+        self.parts = []
+        row = 0
+        for d, a, b in zip(devices, cuts[:-1], cuts[1:]):
+            if b <= a:
+                continue
+            with torch.cuda.device(d):
+                plan = plan_for(coefs, d)
+                pipe = WindowPipeline(plan, lengths[a:b], bases[a:b], **kw)
+            self.parts.append(dict(device=d, pipe=pipe, s0=int(cum[a]), s1=int(cum[b]), r0=row, r1=row + pipe.n_windows))
+            row += pipe.n_windows
+        self.n_windows = row
+
+    def run(self, wave_host, out_host):
+        for part in self.parts:
+            with torch.cuda.device(part["device"]):
+                part["pipe"].run(wave_host[part["s0"]:part["s1"]], out_host[part["r0"]:part["r1"]])
+        for part in self.parts:
+            torch.cuda.synchronize(part["device"])
+        return out_host
+
+
 # ---- plan cache for the numpy-in / numpy-out drop-in functions -----------------------------
 _plans = {}
 _plans_lock = threading.Lock()
