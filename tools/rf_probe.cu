@@ -29,12 +29,16 @@ __global__ void __launch_bounds__(256) probe(float* out, int iters, const float*
                 if (T == 5) a[i] = __ffma2_rn(make_float2(s[0], s[0]), c[i], a[i]);    // reused scalar + 2 pairs
                 if (T == 6) a[i] = __ffma2_rn(make_float2(s[0], s[0]), make_float2(s[1], s[1]), a[i]);  // 2 reused + pair
                 if (T == 7) a[i] = __ffma2_rn(make_float2(s[i], s[i]), a[(i + 3) & 7], a[i]);  // kernel-like: scalar, other state, self
+                if (T == 8) {  // two independent streams sharing each coefficient back to back (reuse cache?)
+                    a[i] = __ffma2_rn(make_float2(s[i], s[i]), c[i], a[i]);
+                    b[i] = __ffma2_rn(make_float2(s[i], s[i]), c[(i + 1) & 7], b[i]);
+                }
             }
         }
     }
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc += a[i].x + a[i].y;
+    for (int i = 0; i < 8; ++i) acc += a[i].x + a[i].y + b[i].x + b[i].y;
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
@@ -79,5 +83,6 @@ int main() {
     printf("T5 ffma2 reused scalar,pair,pair: %.3f of peak\n", run<5>(out, in, blocks, iters, 2.0) / peak);
     printf("T6 ffma2 2 reused scalars,pair : %.3f of peak\n", run<6>(out, in, blocks, iters, 2.0) / peak);
     printf("T7 ffma2 scalar,state,self     : %.3f of peak\n", run<7>(out, in, blocks, iters, 2.0) / peak);
+    printf("T8 2 streams sharing the scalar: %.3f of peak\n", run<8>(out, in, blocks, iters, 4.0) / peak);
     return 0;
 }
