@@ -62,7 +62,7 @@ def GenerateInputData(labelFile=None, inputFile=None, LPF=False, CUTOFF=100):
     inputData = numpy.zeros((totalTimePoints, DOTSPERINPUT, NCHANNELS), dtype=numpy.float32)
     print("Output shape:", inputData.shape)
     currentEntry = 0
-    coefs = None
+    fused = []  # (first row, wav path, timepoints): utterances without a saved envelope
     for currentFileIndex, file in enumerate(files):
         timepoints = filesAndTimepointsDict[file]
         path = os.path.join('resources', 'f2cnn', file)
@@ -72,21 +72,30 @@ def GenerateInputData(labelFile=None, inputFile=None, LPF=False, CUTOFF=100):
             if envelopes.shape[0] != NCHANNELS:
                 raise ValueError("could not broadcast input array from shape ({},) into shape ({},)".format(
                     envelopes.shape[0], NCHANNELS))
-            rows = api.gather_windows_from_matrix(envelopes, timepoints, RADIUS, STEP)
+            inputData[currentEntry:currentEntry + len(timepoints)] = api.gather_windows_from_matrix(
+                envelopes, timepoints, RADIUS, STEP)
         else:
             wavPath = path[:-len('.ENV1.npy')] + '.WAV'
             if not os.path.isfile(wavPath):
                 raise FileNotFoundError(2, 'No such file or directory', path)
-            from .GammatoneFiltering import GetArrayFromWAV
-            from ...gammatone import filters
-            _, wav = GetArrayFromWAV(wavPath)
-            if coefs is None:
-                low = config.getint('FILTERBANK', 'LOW_FREQ')
-                coefs = filters.make_erb_filters(FRAMERATE, filters.centre_freqs(FRAMERATE, NCHANNELS, low))
-            rows = api.features_to_windows([wav], coefs, [timepoints], LPF, CUTOFF, RADIUS, STEP)
-        inputData[currentEntry:currentEntry + len(timepoints)] = rows
+            fused.append((currentEntry, wavPath, timepoints))
         currentEntry += len(timepoints)
         print("\t\t{:<50} done !  {}/{} Files".format(path, currentFileIndex + 1, len(files)))
+    if fused:
+        # one batched launch sequence for every utterance that has no .ENV1.npy: waveform ->
+        # filterbank -> envelope -> windows without the 98 MB/utterance intermediates
+        from concurrent.futures import ThreadPoolExecutor
+        from .GammatoneFiltering import GetArrayFromWAV
+        from ...gammatone import filters
+        low = config.getint('FILTERBANK', 'LOW_FREQ')
+        coefs = filters.make_erb_filters(FRAMERATE, filters.centre_freqs(FRAMERATE, NCHANNELS, low))
+        with ThreadPoolExecutor(max_workers=8) as pool:
+            wavs = [w for _, w in pool.map(GetArrayFromWAV, [f[1] for f in fused])]
+        rows = api.features_to_windows(wavs, coefs, [f[2] for f in fused], LPF, CUTOFF, RADIUS, STEP)
+        pos = 0
+        for first, _, tps in fused:
+            inputData[first:first + len(tps)] = rows[pos:pos + len(tps)]
+            pos += len(tps)
     print('Generated Input Matrix of shape {}.'.format(inputData.shape))
 
     savePath = inputFile or (
