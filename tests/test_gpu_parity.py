@@ -411,3 +411,47 @@ def test_long_stream_config4_full_length(gpu, oracle):
     want = eo[:, ::160].T
     scale = np.sqrt(np.mean(eo ** 2, axis=1))[None, :]
     assert np.max(np.abs(dec[:, sub] - want) / scale) <= TOL
+
+
+def test_fuzz_random_shapes(gpu, oracle):
+    """Seeded fuzz over lengths (incl. rings shorter than a tile and powers of two), channel
+    counts, sample dtypes, cut-offs, decimation grids and time-chunk targets, in ragged batches."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    rng = np.random.default_rng(2024)
+    special = [255, 256, 257, 1023, 1024, 4096, 8191, 8192, 32768, 32769]
+    for case in range(16):
+        C = int(rng.choice([1, 5, 32, 33, 64, 100, 128, 129, 200]))
+        fs = int(rng.choice([16000, 16000, 8000, 22050]))
+        co = filters.make_erb_filters(fs, filters.centre_freqs(fs, C, int(rng.choice([50, 100, 200]))))
+        U = int(rng.integers(1, 5))
+        lens = [int(rng.choice(special)) if rng.random() < 0.4 else int(rng.integers(300, 40000)) for _ in range(U)]
+        dtype = [np.int16, np.float32, np.float64][int(rng.integers(0, 3))]
+        waves = [synth.white_noise_i16(n, seed=1000 * case + i).astype(dtype) for i, n in enumerate(lens)]
+        lpf = bool(rng.random() < 0.7)
+        cutoff = float(rng.choice([20, 50, 100, 400]))
+        step = int(rng.choice([160, 80, 100, 7]))
+        phase = int(rng.integers(0, step))
+        target = int(rng.choice([0, 1, 16, 512]))
+        plan = engine.plan_for(co)
+        batch = plan.batch(lens, step=step, phase=phase, target_items=target)
+        flat = torch.from_numpy(np.concatenate(waves)).cuda()
+        res = batch.run(flat, lpf=lpf, cutoff=cutoff, gfb=torch.float64, env=torch.float64, dec=True)
+        dec_only = batch.run(flat, lpf=lpf, cutoff=cutoff, dec=True)["dec"].cpu().numpy()
+        gfb_all, env_all, dec_all = res["gfb"].cpu().numpy(), res["env"].cpu().numpy(), res["dec"].cpu().numpy()
+        off = 0
+        tag = (case, C, fs, lens, dtype.__name__, lpf, cutoff, step, phase, target)
+        for u, (n, w) in enumerate(zip(lens, waves)):
+            go = oracle.erb_filterbank(w, co)
+            eo = oracle.extract_envelope(go, lpf, cutoff)
+            gfb = gfb_all[C * off:C * (off + n)].reshape(C, n)
+            env = env_all[C * off:C * (off + n)].reshape(C, n)
+            sg = np.maximum(np.sqrt(np.mean(go ** 2, axis=1)), 1e-3 * np.abs(go).max())
+            se = np.maximum(np.sqrt(np.mean(eo ** 2, axis=1)), 1e-3 * np.abs(eo).max())
+            assert rel_err(gfb, go, sg).max() <= TOL, tag
+            assert rel_err(env, eo, se).max() <= TOL, tag
+            f0, f1 = batch.frame_offsets[u], batch.frame_offsets[u + 1]
+            assert f1 - f0 == len(range(phase, n, step)), tag
+            assert np.array_equal(dec_all[f0:f1], env[:, phase::step].astype(np.float32).T), tag
+            assert np.max(np.abs(dec_only[f0:f1] - eo[:, phase::step].T) / se[None, :]) <= TOL, tag
+            off += n
