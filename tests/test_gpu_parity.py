@@ -455,3 +455,24 @@ def test_fuzz_random_shapes(gpu, oracle):
             assert np.array_equal(dec_all[f0:f1], env[:, phase::step].astype(np.float32).T), tag
             assert np.max(np.abs(dec_only[f0:f1] - eo[:, phase::step].T) / se[None, :]) <= TOL, tag
             off += n
+
+
+def test_warmup_lengths_are_what_keeps_truncation_below_float32(gpu, oracle):
+    """f2_plan_set_warmup: the defaults derived from the slowest pole hold parity; cutting the
+    history to 256 samples visibly breaks it (so the truncated-history design is load-bearing and
+    its lengths are not arbitrary)."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = coefs128()
+    w = synth.white_noise_i16(30000, seed=12)
+    _, eo, _ = oracle.utterance(w, co, True, 50)
+    plan = engine.Plan(co)  # private plan: the cached one must keep its defaults
+    wi, we, wc = plan.get_warmup()
+    assert (wi, we, wc) == (1536, 2048, 2048)  # 21.5 / -ln r and 29 / -ln r for r = 0.98590, tile-rounded
+    wd = torch.from_numpy(w).cuda()
+    good = plan.batch([30000], target_items=8).run(wd, lpf=True, cutoff=50, env=torch.float64)["env"].cpu().numpy()
+    assert rel_err(good.reshape(128, -1), eo).max() <= TOL
+    plan.set_warmup(256, 256, 256)
+    assert plan.get_warmup() == (256, 256, 256)
+    bad = plan.batch([30000], target_items=8).run(wd, lpf=True, cutoff=50, env=torch.float64)["env"].cpu().numpy()
+    assert rel_err(bad.reshape(128, -1), eo).max() > 10 * TOL
