@@ -63,8 +63,14 @@ __device__ __forceinline__ float2 load_pair(const void* base, int dtype, long lo
         switch (dtype) {
             case F2_DT_I16: {
                 const short* p = reinterpret_cast<const short*>(base) + off + t;
-                a = (float)p[0];
-                if (two) b = (float)p[1];
+                if (two && (reinterpret_cast<size_t>(p) & 3) == 0) {  // aligned pair: one 32-bit load
+                    const int v = __ldg(reinterpret_cast<const int*>(p));
+                    a = (float)(short)(v & 0xffff);
+                    b = (float)(short)(v >> 16);
+                } else {
+                    a = (float)p[0];
+                    if (two) b = (float)p[1];
+                }
                 break;
             }
             case F2_DT_F32: {

@@ -60,4 +60,18 @@ def eval_path():
 ms = timed(eval_path, reps=5)
 out["config5_eval_frontend_plus_cnn"] = {"frames": 48000 - 1760, "device_ms": ms,
                                          "note": "reference: 25 s Python framing + 0.9 s normalise per utterance before Keras"}
+# ---- full-rate output modes (HBM-bound per SURVEY.md 8d): 256 corpus utterances ----
+lengths = synth.corpus_lengths(256, seed=1)
+flat, _ = synth.corpus_waves_i16(lengths, seed=1)
+fd = torch.from_numpy(flat).cuda()
+bq = plan.batch(lengths)
+cs = 128.0 * float(lengths.sum())
+for tag, kw, bytes_per_cs in (("env_t_f32_time_major", dict(env_t=True), 4.04),
+                              ("gfb_env_f32_reference_layout", dict(gfb=torch.float32, env=torch.float32), 8.04),
+                              ("gfb_env_f64_reference_layout", dict(gfb=torch.float64, env=torch.float64), 16.04)):
+    res = bq.run(fd, lpf=True, cutoff=50, **kw)
+    ms = timed(lambda: bq.run(fd, lpf=True, cutoff=50, out=res, **kw), reps=3, warm=1)
+    out["fullrate_" + tag] = {"device_ms": ms, "channel_samples_per_s": cs / ms * 1e3,
+                              "algorithmic_GBps": bytes_per_cs * cs / ms / 1e6}
+    del res
 print(json.dumps(out, indent=1))
