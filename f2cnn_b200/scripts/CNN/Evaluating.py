@@ -1,190 +1,215 @@
-"""Drop-in for the feature front end of the reference's scripts/CNN/Evaluating.py.
+"""GPU front end behind the names of the reference's scripts/CNN/Evaluating.py.
 
-EvaluateOneWavArray (reference :27-113) spends 25 s per 3 s utterance in a pure-Python dense
-framing loop (:70-78) and ~1 s in per-frame normalizeInput (:79-80); here filterbank, envelope,
-framing and normalisation are one GPU launch sequence (api.dense_frames).  Model loading,
-prediction, the accuracy heuristic and plotting are Keras / matplotlib code of the reference
-and are called exactly as the reference calls them (lazy imports; they need the reference tree
-and its dependencies)."""
+What the reference does per utterance (EvaluateOneWavArray, reference :27-113): filterbank and
+envelope, then 25 s of pure-Python dense framing (:70-78), ~1 s of per-frame normalizeInput
+(:79-80), then Keras prediction, an accuracy heuristic and a matplotlib figure.  Here the first
+three are one GPU launch sequence (api.dense_frames, 0.7 ms of device time for a 3 s
+utterance); prediction and plotting still belong to the reference tree and to Keras and are
+imported lazily, exactly where the reference needs them.
+
+Public names, signatures, defaults and side effects (files written under OutputWavFiles/,
+graphs/) follow the reference; the bodies are organised around small helpers.
+"""
 import glob
 import os
+import shutil
 import time
+from collections import namedtuple
 from configparser import ConfigParser
-from shutil import copyfile
 
 import numpy
 
 from ...gammatone import filters
 from ..processing.GammatoneFiltering import GetArrayFromWAV
 
+_Settings = namedtuple("_Settings", "radius dots period_us nchannels lowfreq framerate")
+
+
+def _settings():
+    """configF2CNN.conf of the working directory (the reference re-reads it in every driver)."""
+    cfg = ConfigParser()
+    cfg.read('configF2CNN.conf')
+    radius = cfg.getint('CNN', 'RADIUS')
+    return cfg, _Settings(radius, 2 * radius + 1, cfg.getint('CNN', 'SAMPLING_PERIOD'),
+                          cfg.getint('FILTERBANK', 'NCHANNELS'), cfg.getint('FILTERBANK', 'LOW_FREQ'),
+                          cfg.getint('FILTERBANK', 'FRAMERATE'))
+
+
+def _bank(framerate, st, centre, coefs):
+    """Filterbank of the call, designed on demand like reference :42-49."""
+    if centre is None:
+        centre = filters.centre_freqs(framerate, st.nchannels, st.lowfreq)
+        coefs = filters.make_erb_filters(framerate, centre)
+    return centre, coefs
+
 
 def SNRdbToSNRlinear(SNRdb):
-    """Reference :180-181 (a power ratio, applied to an amplitude by the caller -- kept)."""
+    """dB -> ratio, reference :180-181.  It is a power ratio that the caller applies to an
+    amplitude; kept as is."""
     return 10 ** (SNRdb / 10.0)
 
 
 def RMS(signal):
-    """Reference :184-190.  numpy.square keeps the input dtype: on an int16 WAV array the
-    squares overflow, exactly like the reference."""
+    """Root mean square, reference :184-190.  numpy.square keeps the dtype of an int16 WAV array,
+    so the squares wrap around exactly as they do in the reference."""
     return numpy.sqrt(numpy.mean(numpy.square(signal)))
+
+
+def MixNoise(wavList, SNRdB):
+    """White Gaussian noise of standard deviation RMS(wav) / SNRdbToSNRlinear(SNRdB) added to the
+    waveform: float64 output (reference :199-200)."""
+    sigma = RMS(wavList) / SNRdbToSNRlinear(SNRdB)
+    return numpy.random.normal(scale=sigma, size=wavList.shape[0]) + wavList
 
 
 def PrepareInputFromArray(wavArray, framerate, config, LPF=False, CUTOFF=100, CENTER_FREQUENCIES=None,
                           FILTERBANK_COEFFICIENTS=None):
-    """The hot part of EvaluateOneWavArray (:42-81): returns (input_data (nb, 2R+1, C) float64
-    normalised per frame, CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS, STEP)."""
+    """Everything between the waveform and model.predict: (nb, 2R+1, C) float64 frames, each
+    log-min-max normalised, nb = n - (2R+1)*STEP (reference :52-80).  Also returns the bank."""
     from ... import api
-    RADIUS = config.getint('CNN', 'RADIUS')
-    SAMPPERIOD = config.getint('CNN', 'SAMPLING_PERIOD')
-    USTOS = 1 / 1000000.
-    if CENTER_FREQUENCIES is None:
-        NCHANNELS = config.getint('FILTERBANK', 'NCHANNELS')
-        lowcutoff = config.getint('FILTERBANK', 'LOW_FREQ')
-        CENTER_FREQUENCIES = filters.centre_freqs(framerate, NCHANNELS, lowcutoff)
-        FILTERBANK_COEFFICIENTS = filters.make_erb_filters(framerate, CENTER_FREQUENCIES)
-    STEP = int(framerate * SAMPPERIOD * USTOS)
+    radius = config.getint('CNN', 'RADIUS')
+    step = int(framerate * config.getint('CNN', 'SAMPLING_PERIOD') * 1e-6)
+    st = _Settings(radius, 2 * radius + 1, 0, config.getint('FILTERBANK', 'NCHANNELS'),
+                   config.getint('FILTERBANK', 'LOW_FREQ'), framerate)
+    centre, coefs = _bank(framerate, st, CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS)
     print("Applying filterbank...")
-    if not LPF:
-        print("Extracting Envelope...")
-    else:
-        print("Extraction Envelope with {}Hz Low Pass Filter...".format(CUTOFF))
-    print(LPF, CUTOFF)
+    print("Extraction Envelope with {}Hz Low Pass Filter...".format(CUTOFF) if LPF else "Extracting Envelope...")
     print("Generating input data for CNN...")
-    input_data = api.dense_frames(wavArray, FILTERBANK_COEFFICIENTS, LPF, CUTOFF, RADIUS, STEP, normalize=True,
-                                  dtype=numpy.float64)
-    print("INPUT SHAPE:", input_data.shape)
-    return input_data, CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS, STEP
+    frames = api.dense_frames(wavArray, coefs, LPF, CUTOFF, radius, step, normalize=True, dtype=numpy.float64)
+    print("INPUT SHAPE:", frames.shape)
+    return frames, centre, coefs, step
+
+
+def _decisions(scores):
+    """1 = rising when the second score wins (reference :87)."""
+    return [1 if s[1] > s[0] else 0 for s in scores]
+
+
+def _label_accuracy(labels, decisions, step):
+    """The reference's heuristic (:92-110): a frame index strictly between two consecutive label
+    timepoints and closer than STEP to one of them is scored against the nearer label (ties go
+    to the earlier one).  Raises ZeroDivisionError when no frame qualifies, like the reference."""
+    times = [l[0] for l in labels]
+    classes = [l[1] for l in labels]
+    hits = 0
+    counted = 0
+    for frame, decided in enumerate(decisions):
+        for left in range(len(labels) - 1):
+            lo, hi = times[left], times[left + 1]
+            if not (lo < frame < hi):
+                continue
+            d_lo, d_hi = abs(frame - lo), abs(frame - hi)
+            if d_lo >= step and d_hi >= step:
+                continue
+            target = classes[left] if d_lo <= d_hi else classes[left + 1]
+            hits += 1 if decided == target else 0
+            counted += 1
+    return hits / counted
 
 
 def EvaluateOneWavArray(wavArray, framerate, wavFileName, model='last_trained_model', LPF=False, CUTOFF=100,
                         CENTER_FREQUENCIES=None, FILTERBANK_COEFFICIENTS=None):
-    """Reference :27-113."""
+    """One waveform through front end, CNN and figure (reference :27-113)."""
     from ... import api
-    from scripts.processing.LabelDataGenerator import ExtractLabel          # reference tree
-    from scripts.processing.FBFileReader import ExtractFBFile               # reference tree
-    from scripts.processing.PHNFileReader import ExtractPhonemes            # reference tree
-    from scripts.plotting.PlottingCNN import PlotEnvelopesAndCNNResultsWithPhonemes  # reference tree
-    config = ConfigParser()
-    config.read('configF2CNN.conf')
-    RADIUS = config.getint('CNN', 'RADIUS')
-    NCHANNELS = config.getint('FILTERBANK', 'NCHANNELS')
-    DOTSPERINPUT = RADIUS * 2 + 1
+    # reference-tree pieces (labels, file readers, figure): resolved at call time
+    from scripts.processing.LabelDataGenerator import ExtractLabel
+    from scripts.processing.FBFileReader import ExtractFBFile
+    from scripts.processing.PHNFileReader import ExtractPhonemes
+    from scripts.plotting.PlottingCNN import PlotEnvelopesAndCNNResultsWithPhonemes
 
-    labels = ExtractLabel(wavFileName, config)
-    labels = [(entry[-4], entry[-1]) for entry in labels] if labels is not None else None
+    cfg, st = _settings()
+    found = ExtractLabel(wavFileName, cfg)
+    labels = None if found is None else [(row[-4], row[-1]) for row in found]
 
-    input_data, CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS, STEP = PrepareInputFromArray(
-        wavArray, framerate, config, LPF, CUTOFF, CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS)
-    nb = input_data.shape[0]
-    # the plots need the full-rate envelopes too (:108)
-    envelopes = api.filterbank_envelope(wavArray, FILTERBANK_COEFFICIENTS, LPF, CUTOFF)
+    frames, centre, coefs, step = PrepareInputFromArray(wavArray, framerate, cfg, LPF, CUTOFF, CENTER_FREQUENCIES,
+                                                        FILTERBANK_COEFFICIENTS)
+    envelopes = api.filterbank_envelope(wavArray, coefs, LPF, CUTOFF)  # the figure shows them at full rate
 
+    stem = os.path.splitext(wavFileName)[0]
     print("Extracting Formants...")
-    formants, sampPeriod = ExtractFBFile(os.path.splitext(wavFileName)[0] + '.FB')
+    formants, _ = ExtractFBFile(stem + '.FB')
     print("Extracting Phonemes...")
-    phonemes = ExtractPhonemes(os.path.splitext(wavFileName)[0] + '.PHN')
+    phonemes = ExtractPhonemes(stem + '.PHN')
 
     print("Evaluating the data with the pretrained model...")
     import keras
-    model = keras.models.load_model(model)
-    scores = model.predict(input_data.reshape(nb, DOTSPERINPUT, NCHANNELS, 1), verbose=1)
-    simplified_scores = [1 if score[1] > score[0] else 0 for score in scores]
+    network = keras.models.load_model(model)
+    scores = network.predict(frames.reshape(frames.shape[0], st.dots, st.nchannels, 1), verbose=1)
     keras.backend.clear_session()
-    del model
-    del input_data
-    accuracy = None
-    if labels is not None:
-        accuracy = 0
-        total_valid = 0
-        for timepoint, score in enumerate(simplified_scores):
-            for index in range(len(labels) - 1):
-                before = labels[index][0]
-                after = labels[index + 1][0]
-                if before < timepoint < after and (abs(timepoint - before) < STEP or abs(timepoint - after) < STEP):
-                    if abs(before - timepoint) <= abs(after - timepoint):
-                        if score == labels[index][1]:
-                            accuracy += 1
-                    else:
-                        if score == labels[index + 1][1]:
-                            accuracy += 1
-                    total_valid += 1
-        accuracy /= total_valid
+    del network, frames
+
+    accuracy = _label_accuracy(labels, _decisions(scores), step) if labels is not None else None
     print("Plotting...")
-    PlotEnvelopesAndCNNResultsWithPhonemes(envelopes, scores, accuracy, CENTER_FREQUENCIES, phonemes, formants,
-                                           wavFileName)
+    PlotEnvelopesAndCNNResultsWithPhonemes(envelopes, scores, accuracy, centre, phonemes, formants, wavFileName)
 
 
 def EvaluateOneWavFile(file, LPF=False, CUTOFF=50, model='last_trained_model', CENTER_FREQUENCIES=None,
                        FILTERBANK_COEFFICIENTS=None):
-    """Reference :116-137."""
+    """Read one .WAV (RIFF or NIST SPHERE) and evaluate it (reference :116-137)."""
     print('Using model', model)
     print("File:\t\t{}".format(file))
-    framerate, wavArray = GetArrayFromWAV(file)
-    EvaluateOneWavArray(wavArray=wavArray, framerate=framerate, LPF=LPF, CUTOFF=CUTOFF, wavFileName=file, model=model,
+    rate, samples = GetArrayFromWAV(file)
+    EvaluateOneWavArray(samples, rate, file, model=model, LPF=LPF, CUTOFF=CUTOFF,
                         CENTER_FREQUENCIES=CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS=FILTERBANK_COEFFICIENTS)
     print("\t\t{}\tdone !".format(file))
 
 
 def EvaluateRandom(count=None, LPF=False, CUTOFF=50):
-    """Reference :140-177."""
+    """Evaluate the organised .WAV files in random order, all of them or `count` draws with
+    replacement (reference :140-177)."""
     os.environ['TF_CPP_MIN_LOG_LEVEL'] = '3'
-    TotalTime = time.time()
+    started = time.time()
     if not os.path.isdir("graphs"):
-        os.mkdir('graphs')
-        os.mkdir(os.path.join('graphs', 'FallingOrRising'))
-    wavFiles = glob.glob(os.path.join('resources', 'f2cnn', '*', '*.WAV'))
+        os.makedirs(os.path.join('graphs', 'FallingOrRising'))
+    candidates = glob.glob(os.path.join('resources', 'f2cnn', '*', '*.WAV'))
+    # like the reference, the banner indexes the list before the emptiness check
     print("\n###############################\nEvaluating network on {} WAV files in '{}'.".format(
-        len(wavFiles), os.path.split(wavFiles[0])[0]))
-    if not wavFiles:
+        len(candidates), os.path.split(candidates[0])[0]))
+    if not candidates:
         print("NO WAV FILES FOUND")
         exit(-1)
-    config = ConfigParser()
-    config.read('configF2CNN.conf')
-    framerate = config.getint('FILTERBANK', 'FRAMERATE')
-    nchannels = config.getint('FILTERBANK', 'NCHANNELS')
-    lowcutoff = config.getint('FILTERBANK', 'LOW_FREQ')
-    CENTER_FREQUENCIES = filters.centre_freqs(framerate, nchannels, lowcutoff)
-    FILTERBANK_COEFFICIENTS = filters.make_erb_filters(framerate, CENTER_FREQUENCIES)
+    _, st = _settings()
+    centre, coefs = _bank(st.framerate, st, None, None)
     if count is None:
-        numpy.random.shuffle(wavFiles)
+        numpy.random.shuffle(candidates)
     elif count > 1:
-        wavFiles = numpy.random.choice(wavFiles, count)
-    for file in wavFiles:
-        EvaluateOneWavFile(file, LPF=LPF, CUTOFF=CUTOFF, CENTER_FREQUENCIES=CENTER_FREQUENCIES,
-                           FILTERBANK_COEFFICIENTS=FILTERBANK_COEFFICIENTS)
+        candidates = numpy.random.choice(candidates, count)
+    for path in candidates:
+        EvaluateOneWavFile(path, LPF=LPF, CUTOFF=CUTOFF, CENTER_FREQUENCIES=centre, FILTERBANK_COEFFICIENTS=coefs)
     print("Evaluating network on all files.")
-    print('              Total time:', time.time() - TotalTime)
+    print('              Total time:', time.time() - started)
     print('')
 
 
-def MixNoise(wavList, SNRdB):
-    """Reference :199-200: noise = normal(scale=RMS(wav)/10^(dB/10)); output = noise + wav (float64)."""
-    noise = numpy.random.normal(scale=RMS(wavList) / SNRdbToSNRlinear(SNRdB), size=wavList.shape[0])
-    return noise + wavList
+def _copy_sidecars(src_stem, dst_stem):
+    """.FB / .PHN / .WRD next to the noisy copy, if the originals exist (reference :210-216)."""
+    try:
+        for ext in ('.FB', '.PHN', '.WRD'):
+            shutil.copyfile(src_stem + ext, dst_stem + ext)
+    except FileNotFoundError as err:
+        print(err.strerror)
+        print("No .FB or .PHN or .WRD files.")
 
 
 def EvaluateWithNoise(file, LPF=False, CUTOFF=100, model='last_trained_model', CENTER_FREQUENCIES=None,
                       FILTERBANK_COEFFICIENTS=None, SNRdB=-3):
-    """Reference :193-221."""
+    """Add noise at SNRdB, save OutputWavFiles/addedNoise/<name><SNR>dB.WAV (float64 samples, as
+    the reference writes them) with its sidecar files, then evaluate it (reference :193-221)."""
     from scipy.io import wavfile
     print("File:\t\t{}".format(file))
     print("Appyling gaussian noise, new SNR is {SNR}dB".format(SNR=SNRdB))
-    framerate, wavList = GetArrayFromWAV(file)
-    output = MixNoise(wavList, SNRdB)
-    os.makedirs(os.path.join('OutputWavFiles', 'addedNoise'), exist_ok=True)
-    baseName = os.path.join('OutputWavFiles', 'addedNoise',
-                            os.path.split(os.path.splitext(file)[0])[1]) + '{SNR}dB'.format(SNR=SNRdB)
-    newPath = baseName + '.WAV'
-    srcBasename = os.path.splitext(file)[0]
-    wavfile.write(newPath, framerate, output)
-    try:
-        copyfile(srcBasename + '.FB', baseName + '.FB')
-        copyfile(srcBasename + '.PHN', baseName + '.PHN')
-        copyfile(srcBasename + '.WRD', baseName + '.WRD')
-    except FileNotFoundError as e:
-        print(e.strerror)
-        print("No .FB or .PHN or .WRD files.")
-    print('New noisy WAVE file saved as', newPath)
-    EvaluateOneWavArray(output, framerate, newPath, model=model, LPF=LPF, CUTOFF=CUTOFF,
+    rate, clean = GetArrayFromWAV(file)
+    noisy = MixNoise(clean, SNRdB)
+
+    out_dir = os.path.join('OutputWavFiles', 'addedNoise')
+    os.makedirs(out_dir, exist_ok=True)
+    src_stem = os.path.splitext(file)[0]
+    dst_stem = os.path.join(out_dir, os.path.basename(src_stem)) + '{SNR}dB'.format(SNR=SNRdB)
+    noisy_path = dst_stem + '.WAV'
+    wavfile.write(noisy_path, rate, noisy)
+    _copy_sidecars(src_stem, dst_stem)
+    print('New noisy WAVE file saved as', noisy_path)
+
+    EvaluateOneWavArray(noisy, rate, noisy_path, model=model, LPF=LPF, CUTOFF=CUTOFF,
                         CENTER_FREQUENCIES=CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS=FILTERBANK_COEFFICIENTS)
     print("\t\t{}\tdone !".format(file))

@@ -99,3 +99,76 @@ def test_array_functions(oracle):
     assert np.max(np.abs(lp - oracle.low_pass_filter(np.abs(want), 50))) <= TOL * np.sqrt(np.mean(np.abs(want) ** 2))
     env = EE.ExtractEnvelopeFromMatrix(gfb)  # defaults: LPF=False
     assert rel(env, oracle.extract_envelope(gfb, False)) <= TOL
+    # lfilter(axis=0) semantics on a 2-D array: every column is one signal
+    cols = np.abs(gfb[:3]).T.copy()
+    lp2 = EE.lowPassFilter(cols, 120)
+    assert lp2.shape == cols.shape
+    for j in range(3):
+        wantj = oracle.low_pass_filter(cols[:, j].copy(), 120)
+        assert np.max(np.abs(lp2[:, j] - wantj)) <= TOL * np.sqrt(np.mean(wantj ** 2))
+
+
+def test_evaluating_front_end_and_driver(tree, oracle, monkeypatch):
+    """scripts.CNN.Evaluating: frames handed to model.predict match the reference's framing +
+    normalizeInput of the float64 envelopes; the driver calls predict/plot with them (Keras and
+    the reference-tree readers are stand-ins: they are outside the hot path)."""
+    import sys
+    import types
+    from configparser import ConfigParser
+    tmp_path, waves = tree
+    from f2cnn_b200 import dropin
+    from f2cnn_b200.gammatone import filters
+    dropin.install()
+    try:
+        from scripts.CNN import Evaluating
+        cfg = ConfigParser()
+        cfg.read("configF2CNN.conf")
+        w = waves[("TEST", "DR1.SPK2.SI3")]
+        frames, centre, co, step = Evaluating.PrepareInputFromArray(w, 16000, cfg, True, 50)
+        assert step == 160 and frames.dtype == np.float64 and frames.shape == (len(w) - 11 * 160, 11, 32)
+        assert np.array_equal(centre, filters.centre_freqs(16000, 32, 100))
+        _, eo, _ = oracle.utterance(w, co, True, 50)
+        pick = [0, 1, 777, frames.shape[0] - 1]
+        want = np.stack([oracle.normalize_input(oracle.dense_frames(eo, 5, 160, i, i + 1)[0]) for i in pick])
+        assert np.max(np.abs(frames[pick] - want)) <= 2e-3  # log-min-max domain, see test_gpu_parity evalnoise case
+
+        seen = {}
+
+        class _Net:
+            def predict(self, x, verbose=0):
+                seen["x"] = x
+                return np.stack([np.linspace(0, 1, x.shape[0]), np.linspace(1, 0, x.shape[0])], axis=1)
+
+        keras = types.ModuleType("keras")
+        keras.models = types.SimpleNamespace(load_model=lambda name: _Net())
+        keras.backend = types.SimpleNamespace(clear_session=lambda: None)
+        monkeypatch.setitem(sys.modules, "keras", keras)
+        stubs = {
+            "scripts.processing.LabelDataGenerator": dict(ExtractLabel=lambda name, c: [[0, 0, 0, 0, 0, 1000, 0, 0, 1],
+                                                                                       [0, 0, 0, 0, 0, 1200, 0, 0, 0]]),
+            "scripts.processing.FBFileReader": dict(ExtractFBFile=lambda name: (np.zeros((3, 4)), 100)),
+            "scripts.processing.PHNFileReader": dict(ExtractPhonemes=lambda name: [("aa", 0, 10)]),
+            "scripts.plotting": {},
+            "scripts.plotting.PlottingCNN": dict(PlotEnvelopesAndCNNResultsWithPhonemes=lambda *a: seen.update(plot=a)),
+        }
+        for name, attrs in stubs.items():
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            if not attrs:
+                m.__path__ = []
+            monkeypatch.setitem(sys.modules, name, m)
+        Evaluating.EvaluateOneWavArray(w, 16000, "x.WAV", LPF=True, CUTOFF=50)
+        assert seen["x"].shape == (frames.shape[0], 11, 32, 1) and np.array_equal(seen["x"][..., 0], frames)
+        envs, scores, acc, cf = seen["plot"][:4]
+        assert envs.shape == (32, len(w)) and rel(envs, eo) <= TOL and scores.shape == (frames.shape[0], 2)
+        # scores cross at the middle frame: decisions 0 before it; frames 1001..1159 -> label 1 (misses),
+        # 1041..1199 -> nearer label decides; just check against the restated rule
+        dec = [int(s[1] > s[0]) for s in scores]
+        good = n = 0
+        for t, d in enumerate(dec):
+            if 1000 < t < 1200 and min(t - 1000, 1200 - t) < 160:
+                n += 1
+                good += int(d == (1 if t - 1000 <= 1200 - t else 0))
+        assert acc == good / n
+    finally:
+        dropin.uninstall()

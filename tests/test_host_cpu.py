@@ -164,3 +164,68 @@ def test_rms_keeps_the_int16_overflow_quirk():
         assert RMS(x) == np.sqrt(np.mean(np.square(x)))          # squares wrap in int16 like the reference
     assert RMS(x) != pytest.approx(np.sqrt(np.mean(x.astype(np.float64) ** 2)))
     assert SNRdbToSNRlinear(10) == 10.0
+
+
+def _accuracy_restated(labels, decisions, step):
+    """Reference scripts/CNN/Evaluating.py:92-107 restated with explicit sets: frame t counts for
+    the interval (before, after) if it lies strictly inside and is closer than STEP to an end."""
+    good = n = 0
+    for t, d in enumerate(decisions):
+        for (b, cb), (a, ca) in zip(labels[:-1], labels[1:]):
+            if b < t < a and min(t - b, a - t) < step:
+                n += 1
+                good += int(d == (cb if t - b <= a - t else ca))
+    return good / n
+
+
+def test_label_accuracy_heuristic_matches_the_reference_rule():
+    from f2cnn_b200.scripts.CNN.Evaluating import _decisions, _label_accuracy
+    rng = np.random.default_rng(11)
+    for step in (2, 7, 160):
+        times = np.sort(rng.choice(np.arange(5, 4000), size=12, replace=False))
+        labels = [(int(t), int(c)) for t, c in zip(times, rng.integers(0, 2, size=12))]
+        scores = rng.random((4200, 2))
+        dec = _decisions(scores)
+        assert dec == [int(s[1] > s[0]) for s in scores]
+        assert _label_accuracy(labels, dec, step) == _accuracy_restated(labels, dec, step)
+    # equidistant frame goes to the EARLIER label; no qualifying frame -> ZeroDivisionError
+    assert _label_accuracy([(0, 1), (2, 0)], [0, 1, 0], 5) == 1.0
+    with pytest.raises(ZeroDivisionError):
+        _label_accuracy([(0, 1), (1, 0)], [0, 1, 0], 5)
+
+
+def test_mix_noise_draws_like_the_reference_expression():
+    from f2cnn_b200.scripts.CNN.Evaluating import RMS, MixNoise, SNRdbToSNRlinear
+    wav = (np.random.default_rng(5).standard_normal(4000) * 30).astype(np.int16)   # squares stay inside int16
+    np.random.seed(1234)
+    with np.errstate(over="ignore"):
+        got = MixNoise(wav, -3)
+        np.random.seed(1234)
+        want = np.random.normal(scale=RMS(wav) / SNRdbToSNRlinear(-3), size=wav.shape[0]) + wav
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+
+
+def test_input_generator_label_table_and_sphere_reader(tmp_path):
+    from f2cnn_b200.scripts.processing.GammatoneFiltering import GetArrayFromWAV
+    from f2cnn_b200.scripts.processing.InputGenerator import GetListOfEnvelopeFilesAndTimepoints
+    csvp = tmp_path / "labels.csv"
+    csvp.write_text("TRAIN,DR1,FAAA0,SX1,iy,3000,1,2,1\nTEST,DR2,MBBB0,SA2,ae,500,1,2,0\nTRAIN,DR1,FAAA0,SX1,ih,1000,1,2,0\n")
+    table = GetListOfEnvelopeFilesAndTimepoints(str(csvp))
+    assert table == {os.path.join("TRAIN", "DR1.FAAA0.SX1.ENV1.npy"): [3000, 1000],
+                     os.path.join("TEST", "DR2.MBBB0.SA2.ENV1.npy"): [500]}
+    csvp.write_text("TRAIN,DR1,FAAA0,SX1,iy,3000\n")
+    with pytest.raises(ValueError):
+        GetListOfEnvelopeFilesAndTimepoints(str(csvp))
+    # NIST SPHERE, both byte orders
+    x = (np.arange(-300, 300) * 50).astype(np.int16)
+    for fmt, dt in (("01", "<i2"), ("10", ">i2")):
+        head = ("NIST_1A\n   1024\nsample_count -i {}\nsample_rate -i 16000\nchannel_count -i 1\nsample_n_bytes -i 2\n"
+                "sample_byte_format -s2 {}\nsample_coding -s3 pcm\nend_head\n").format(len(x), fmt).encode()
+        p = tmp_path / ("a%s.WAV" % fmt)
+        p.write_bytes(head.ljust(1024, b" ") + x.astype(dt).tobytes())
+        rate, got = GetArrayFromWAV(str(p))
+        assert rate == 16000 and got.dtype == np.int16 and np.array_equal(got, x)
+    bad = tmp_path / "bad.WAV"
+    bad.write_bytes(b"JUNKJUNKJUNK")
+    with pytest.raises(ValueError):
+        GetArrayFromWAV(str(bad))
