@@ -53,6 +53,8 @@ struct DeviceGuard {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int round_up_tile(double v) { return (int)(ceil(v / f2::kTile) * f2::kTile); }
+constexpr float kDirectMinCyGfb = 0.25f;
+constexpr float kDirectMinCyEnv = 0.035f;
 
 // Per-stage float32 rounding whose SUM over the four stages is as close to 4*c as the
 // float32 lattice allows.  The four sections share their poles, so the first-order error of
@@ -155,14 +157,27 @@ int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** ou
         const double a0n = A0 / B0;
         par[(size_t)f2::P_G4 * c_pad + c] = (float)(a0n * a0n * a0n * a0n / gain);
         for (int s = 0; s < 4; ++s) par[(size_t)(f2::P_Z + s) * c_pad + c] = (float)(k[1 + s] / A0);
-        float cq[4], ncy[4];
+        float cq[4], ncy[4], nb1[4];
         dither4(b2, cq);
         dither4(-(1.0 + b1 + b2), ncy);
+        dither4(-b1, nb1);
         for (int s = 0; s < 4; ++s) {
             par[(size_t)(f2::P_CQ + s) * c_pad + c] = cq[s];
             par[(size_t)(f2::P_NCY + s) * c_pad + c] = ncy[s];
+            par[(size_t)(f2::P_NB1 + s) * c_pad + c] = nb1[s];
         }
         min_nlr = std::min(min_nlr, -0.5 * log(b2));  // -ln(pole radius)
+    }
+    // Per group of 32 channels (one warp of the fused kernel): min of 1 + B1 + B2 = |1 - pole|^2.
+    // The fused kernel runs the direct form (3 FMAs per section) where this is large enough for its
+    // float32 round-off to match the delta form's, and the delta form nearer to z = 1.
+    for (int g0 = 0; g0 < c_pad; g0 += 32) {
+        double cy = 1e300;
+        for (int c = g0; c < std::min(C, g0 + 32); ++c) {
+            const double* k = coefs + (size_t)c * 10;
+            cy = std::min(cy, 1.0 + (k[7] + k[8]) / k[6]);
+        }
+        for (int c = g0; c < g0 + 32; ++c) par[(size_t)f2::P_FORM * c_pad + c] = (float)cy;
     }
     f2_plan* p = new (std::nothrow) f2_plan();
     if (!p) return fail(F2_ERR_INVALID, "out of host memory");
@@ -274,20 +289,22 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
 
     // ---- work items: (utterance, channel block, time chunk) -------------------------------
     const int cblocks = (plan->C + f2::kChanPerBlock - 1) / f2::kChanPerBlock;
-    // Time chunking policy.  Whole utterances when they already give ~1 wave of CTAs (4 resident
-    // CTAs on each of 148 SMs); otherwise chunks, preferably >= 16384 samples (each chunk pays
-    // w_casc (+ w_lpf) samples of warm-up) and a whole number of waves, never below 2048.
+    // Time chunking policy, counted in units of 128 channels (512 such units are resident on the
+    // 148 SMs at a time, whatever the CTA width).  Whole utterances when they already give ~1 wave;
+    // otherwise chunks, preferably >= 16384 samples (each chunk pays w_casc (+ w_lpf) samples of
+    // warm-up) and a whole number of waves, never below 2048.
+    const int units = (plan->C + 127) / 128;
     const long long wave_ctas = 148 * 4;
     long long whole = 0;
-    for (int u = 0; u < n_utts; ++u) whole += lengths[u] > 0 ? cblocks : 0;
+    for (int u = 0; u < n_utts; ++u) whole += lengths[u] > 0 ? units : 0;
     long long seg = (long long)1 << 40;  // no splitting
     if (target_items > 0) {
         if (whole < target_items && wave > 0)
-            seg = (long long)align_up((size_t)std::max<long long>(wave * cblocks / target_items, 2048), f2::kTile);
+            seg = (long long)align_up((size_t)std::max<long long>(wave * units / target_items, 2048), f2::kTile);
     } else if (whole < wave_ctas && wave > 0) {
-        long long best = std::max<long long>(wave * cblocks / wave_ctas, 2048);
+        long long best = std::max<long long>(wave * units / wave_ctas, 2048);
         for (int waves = 4; waves >= 2; --waves) {
-            const long long cand = wave * cblocks / (waves * wave_ctas);
+            const long long cand = wave * units / (waves * wave_ctas);
             if (cand >= 16384) { best = cand; break; }
         }
         seg = (long long)align_up((size_t)best, f2::kTile);
@@ -314,7 +331,7 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         return (a.t1 - a.t0) > (c.t1 - c.t0);
     });
     b->n_items = (long long)items.size();
-    b->n_whole = whole;
+    b->n_whole = whole / units * cblocks;  // same utterance count, in CTAs
 
     // ---- lane streams: (utterance, time chunk), 32 per CTA, kLaneWarps channels per CTA ------
     {
@@ -576,6 +593,11 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     }
     fp.C = plan->C;
     fp.c_pad = plan->c_pad;
+    // Direct-form threshold (measured against the float64 oracle): round-off of
+    // the direct form grows like 1/(1+B1+B2).  The envelope stays at the delta form's error level
+    // (<= 1e-5 of the channel RMS) down to 0.035; the filterbank output itself only down to 0.25.
+    fp.direct_min_cy = a->gfb ? kDirectMinCyGfb : kDirectMinCyEnv;
+    if (const char* v = getenv("F2_DIRECT_MIN_CY")) fp.direct_min_cy = (float)atof(v);  // development knob
     fp.step = b->step;
     fp.phase = b->phase;
     fp.lpf = a->lpf ? 1 : 0;

@@ -16,16 +16,21 @@ namespace f2 {
 
 constexpr int kTile = 256;        // samples per shared-memory tile (divides every ring >= 256)
 constexpr int kStages = 4;        // TMA pipeline depth
-constexpr int kChanPerBlock = 128; // channels (threads) per CTA of the fused kernel
+constexpr int kChanPerBlock = 32;  // channels (threads) per CTA of the fused kernel: one warp
+constexpr int kEdgeChanPerBlock = 128;           // channels (threads) per CTA of the sequential edge kernel
 constexpr int kRingAlign = 256;   // ring allocations are multiples of this many samples
-constexpr int kNumChanPar = 16;   // floats per channel in the parameter block
+constexpr int kNumChanPar = 18;   // floats per channel in the parameter block
 
 // Per-channel parameter block, parameter-major: par[i * c_pad + c].
 //   0      g4      = A0^4 / gain: output scale of the cascade (filters.py:148,174-182,237)
 //   1..4   z[k]    = A1k / A0: the stage's zero           (filters.py:167-170)
 //   5..8   cq[k]   = B2 rounded per stage (dithered)      (filters.py:152)
 //   9..12  ncy[k]  = -(1 + B1 + B2) rounded per stage     (filters.py:151-152)
-enum ChanPar { P_G4 = 0, P_Z = 1, P_CQ = 5, P_NCY = 9 };
+//   13..16 nb1[k]  = -B1 rounded per stage: direct-form feedback (with -cq[k]) for the
+//                    channel groups whose poles are far enough from z = 1
+//   17     group_cy = min over the channel's group of 32 of 1 + B1 + B2 (the fused kernel picks
+//                    the section form per group from it)
+enum ChanPar { P_G4 = 0, P_Z = 1, P_CQ = 5, P_NCY = 9, P_NB1 = 13, P_FORM = 17 };
 
 // One utterance (or one matrix row for the stand-alone envelope path).
 struct UttDesc {

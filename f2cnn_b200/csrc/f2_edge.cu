@@ -57,11 +57,11 @@ __device__ __forceinline__ void store_edge(const float (&z)[4], const float (&cq
     o[1] = n_odd ? make_float4(e1[0], e1[1], e1[2], e1[3]) : make_float4(e0[0], e0[1], e0[2], e0[3]);
 }
 
-__global__ void __launch_bounds__(kChanPerBlock) edge_kernel(const UttDesc* utts, const float* __restrict__ chan,
+__global__ void __launch_bounds__(kEdgeChanPerBlock) edge_kernel(const UttDesc* utts, const float* __restrict__ chan,
                                                              int C, int c_pad, const float2* __restrict__ xz,
                                                              int w_edge, float* __restrict__ edge) {
     const UttDesc ut = utts[blockIdx.x];
-    const int c = blockIdx.y * kChanPerBlock + threadIdx.x;
+    const int c = blockIdx.y * kEdgeChanPerBlock + threadIdx.x;
     if (c >= C || ut.n <= 0) return;
     float z[4], cq[4], ncy[4];
 #pragma unroll
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(kChanPerBlock) edge_kernel(const UttDesc* utts
 cudaError_t launch_edge(const UttDesc* utts, int n_utts, const float* chan, int C, int c_pad, const float2* xz,
                         int w_edge, float* edge, cudaStream_t stream) {
     if (n_utts <= 0) return cudaSuccess;
-    dim3 grid(n_utts, (C + kChanPerBlock - 1) / kChanPerBlock);
-    edge_kernel<<<grid, kChanPerBlock, 0, stream>>>(utts, chan, C, c_pad, xz, w_edge, edge);
+    dim3 grid(n_utts, (C + kEdgeChanPerBlock - 1) / kEdgeChanPerBlock);
+    edge_kernel<<<grid, kEdgeChanPerBlock, 0, stream>>>(utts, chan, C, c_pad, xz, w_edge, edge);
     return cudaGetLastError();
 }
 

@@ -43,10 +43,12 @@
 
 namespace f2 {
 
+// FORM 0 (delta form): cq = B2, ncy = -(1+B1+B2); state q = y[t-1]-y[t-2].
+// FORM 1 (direct form): cq holds -B2, ncy holds -B1;   state q = y[t-2].
 struct Coef {
     float2 z[4];    // A1k/A0 (the stage's zero), broadcast to both halves
-    float2 cq[4];   // B2 per stage
-    float2 ncy[4];  // -(1+B1+B2) per stage
+    float2 cq[4];
+    float2 ncy[4];
     float g4;       // A0^4/gain: the cascade's output scale
 };
 
@@ -71,6 +73,7 @@ __device__ __forceinline__ void reset(State& s) {
 
 // One sample through the packed (real, imag) 4-stage cascade.  e[] = injection
 // coefficients for this sample's parity, g = G[t].
+template <int FORM>
 __device__ __forceinline__ float2 cascade(const Coef& k, State& s, float2 u, float g, const float (&e)[4]) {
     float2 up = s.up;
     s.up = u;
@@ -79,10 +82,17 @@ __device__ __forceinline__ float2 cascade(const Coef& k, State& s, float2 u, flo
         float2 in = __ffma2_rn(k.z[i], up, u);
         in.y = fmaf(e[i], g, in.y);
         const float2 yo = s.y[i];
-        float2 qn = __ffma2_rn(k.cq[i], s.q[i], in);
-        qn = __ffma2_rn(k.ncy[i], yo, qn);
-        const float2 yn = __fadd2_rn(yo, qn);
-        s.q[i] = qn;
+        float2 yn;
+        if (FORM == 0) {
+            float2 qn = __ffma2_rn(k.cq[i], s.q[i], in);
+            qn = __ffma2_rn(k.ncy[i], yo, qn);
+            yn = __fadd2_rn(yo, qn);
+            s.q[i] = qn;
+        } else {
+            const float2 acc = __ffma2_rn(k.cq[i], s.q[i], in);  // in - B2*y[t-2]
+            yn = __ffma2_rn(k.ncy[i], yo, acc);                  //    - B1*y[t-1]
+            s.q[i] = yo;
+        }
         s.y[i] = yn;
         up = yo;
         u = yn;
@@ -91,6 +101,7 @@ __device__ __forceinline__ float2 cascade(const Coef& k, State& s, float2 u, flo
 }
 
 // Real half only (scalar), used for the edge-residual pass.
+template <int FORM>
 __device__ __forceinline__ void cascade_real(const Coef& k, State& s, float u) {
     float up = s.up.x;
     s.up.x = u;
@@ -98,13 +109,40 @@ __device__ __forceinline__ void cascade_real(const Coef& k, State& s, float u) {
     for (int i = 0; i < 4; ++i) {
         const float in = fmaf(k.z[i].x, up, u);
         const float yo = s.y[i].x;
-        float qn = fmaf(k.cq[i].x, s.q[i].x, in);
-        qn = fmaf(k.ncy[i].x, yo, qn);
-        const float yn = yo + qn;
-        s.q[i].x = qn;
+        float yn;
+        if (FORM == 0) {
+            float qn = fmaf(k.cq[i].x, s.q[i].x, in);
+            qn = fmaf(k.ncy[i].x, yo, qn);
+            yn = yo + qn;
+            s.q[i].x = qn;
+        } else {
+            yn = fmaf(k.ncy[i].x, yo, fmaf(k.cq[i].x, s.q[i].x, in));
+            s.q[i].x = yo;
+        }
         s.y[i].x = yn;
         up = yo;
         u = yn;
+    }
+}
+
+// Residuals of the zero-padded ring equation at ring positions n and n+1, from the stage states
+// after sample n-1 (y = y[n-1]; u = the stage's input at n-1), in the scaled stage variables:
+//   e0 = b1*y[n-1] + b2*y[n-2] - z_k*u[n-1]      e1 = b2*y[n-1]
+// FORM 0: b1*y[n-1] + b2*y[n-2] = (cy-1)*y - cq*q with q = y[n-1]-y[n-2];  FORM 1: directly.
+template <int FORM>
+__device__ __forceinline__ void edge_residuals(const Coef& k, const State& s, float (&e0)[4], float (&e1)[4]) {
+    float uprev = s.up.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (FORM == 0) {
+            const float cy = -k.ncy[i].x;
+            e0[i] = fmaf(cy - 1.0f, s.y[i].x, -k.cq[i].x * s.q[i].x) - k.z[i].x * uprev;
+            e1[i] = k.cq[i].x * s.y[i].x;
+        } else {
+            e0[i] = -fmaf(k.ncy[i].x, s.y[i].x, k.cq[i].x * s.q[i].x) - k.z[i].x * uprev;
+            e1[i] = -k.cq[i].x * s.y[i].x;
+        }
+        uprev = s.y[i].x;
     }
 }
 
@@ -134,7 +172,7 @@ __device__ __forceinline__ float envelope(const FusedParams& p, State& s, float2
     return e;
 }
 
-template <int ENV, int OUT, bool ZEROX, int U>
+template <int FORM, int ENV, int OUT, bool ZEROX, int U>
 __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, State& s, const float (&ee)[4],
                                          const float (&eo)[4], const float2* __restrict__ sxz,
                                          const float* __restrict__ sg, int t, int cnt, bool active, OutCtx& o) {
@@ -162,7 +200,7 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const float2 u = make_float2(ZEROX ? 0.f : xv[2 * j], xv[2 * j + 1]);
-            const float2 y = (j & 1) ? cascade(k, s, u, gv[j], eo) : cascade(k, s, u, gv[j], ee);
+            const float2 y = (j & 1) ? cascade<FORM>(k, s, u, gv[j], eo) : cascade<FORM>(k, s, u, gv[j], ee);
             if (ENV > 0) ev[j] = envelope<ENV>(p, s, y);
             if (OUT == 2) {
                 if (o.gfb && active) __stcs(o.gfb + (size_t)j * o.C, k.g4 * y.x);
@@ -188,7 +226,7 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
     for (; i < cnt; ++i) {
         const float2 xz = sxz[i];
         const float2 u = make_float2(ZEROX ? 0.f : xz.x, xz.y);
-        const float2 y = (i & 1) ? cascade(k, s, u, sg[i], eo) : cascade(k, s, u, sg[i], ee);
+        const float2 y = (i & 1) ? cascade<FORM>(k, s, u, sg[i], eo) : cascade<FORM>(k, s, u, sg[i], ee);
         float e = 0.f;
         if (ENV > 0) e = envelope<ENV>(p, s, y);
         if (OUT == 2) {
@@ -209,19 +247,19 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
     }
 }
 
-// EDGE: the edge residuals come from the per-utterance table (time-chunked batches) instead of
-// the in-kernel pass; a template parameter so that the whole-utterance instantiation keeps its
-// register allocation.
-template <int MINB, int U, bool EDGE>
-__global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedParams p) {
-    __shared__ __align__(128) float2 s_xz[kStages][kTile];
-    __shared__ __align__(128) float s_g[kStages][kTile];
-    __shared__ __align__(8) uint64_t s_full[kStages];
+struct Smem {
+    float2 (*xz)[kTile];
+    float (*g)[kTile];
+    uint64_t* full;
+};
 
-    const Item item = p.items[blockIdx.x];
+// The whole CTA (= one warp = 32 adjacent channels) for one section form.
+// EDGE: the edge residuals come from the per-utterance table (time-chunked batches) instead of
+// the in-kernel pass.
+template <int FORM, int U, bool EDGE>
+__device__ __forceinline__ void fused_body(const FusedParams& p, const Item& item, const Smem& sm, const int c) {
     const UttDesc ut = p.utts[item.utt];
     const int tid = threadIdx.x;
-    const int c = item.cblock * kChanPerBlock + tid;
     const bool active = c < p.C;
     const int n = ut.n;
     const int N2 = ut.N2;
@@ -236,8 +274,8 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float z = on * cp[(P_Z + i) * p.c_pad];
-            const float cq = on * cp[(P_CQ + i) * p.c_pad];
-            const float ncy = on * cp[(P_NCY + i) * p.c_pad];
+            const float cq = on * (FORM == 1 ? -cp[(P_CQ + i) * p.c_pad] : cp[(P_CQ + i) * p.c_pad]);
+            const float ncy = on * cp[((FORM == 1 ? P_NB1 : P_NCY) + i) * p.c_pad];
             k.z[i] = make_float2(z, z);
             k.cq[i] = make_float2(cq, cq);
             k.ncy[i] = make_float2(ncy, ncy);
@@ -251,8 +289,7 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     const bool need_env = p.env_t != nullptr || p.dec != nullptr;
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
     const bool full_out = p.gfb_t != nullptr || p.env_t != nullptr;
-    constexpr bool edge_given = EDGE;  // chunked batches: one edge pass per utterance, not per chunk
-    const int nE = (need_imag && !edge_given) ? (n - tE0 + kTile - 1) / kTile : 0;
+    const int nE = (need_imag && !EDGE) ? (n - tE0 + kTile - 1) / kTile : 0;
     const int w_lpf = (p.lpf && need_env) ? p.w_lpf : 0;
     int ts, tenv;
     if (t0 - w_lpf - p.w_casc <= 0) {
@@ -272,16 +309,11 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     auto issue = [&](int kk) {
         const int b = kk % kStages;
         const int tau = tile_time(kk) & mask;
-        mbar_expect_tx(&s_full[b], kTile * 12);
-        tma_load_1d(&s_xz[b][0], xz_ring + tau, kTile * 8, &s_full[b]);
-        tma_load_1d(&s_g[b][0], g_ring + tau, kTile * 4, &s_full[b]);
+        mbar_expect_tx(&sm.full[b], kTile * 12);
+        tma_load_1d(&sm.xz[b][0], xz_ring + tau, kTile * 8, &sm.full[b]);
+        tma_load_1d(&sm.g[b][0], g_ring + tau, kTile * 4, &sm.full[b]);
     };
 
-    if (tid == 0) {
-        for (int b = 0; b < kStages; ++b) mbar_init(&s_full[b], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
     if (big && tid == 0) {
         const int pre = total < kStages ? total : kStages;
         for (int kk = 0; kk < pre; ++kk) issue(kk);
@@ -290,7 +322,7 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     State s;
     reset(s);
     float ee[4] = {0.f, 0.f, 0.f, 0.f}, eo[4] = {0.f, 0.f, 0.f, 0.f};
-    if (edge_given && need_imag && active) {
+    if (EDGE && need_imag && active) {
         const float4* e = reinterpret_cast<const float4*>(p.edge + ((size_t)item.utt * p.C + c) * 8);
         const float4 v0 = __ldg(e), v1 = __ldg(e + 1);
         ee[0] = v0.x; ee[1] = v0.y; ee[2] = v0.z; ee[3] = v0.w;
@@ -314,36 +346,25 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
         const int b = kk % kStages;
         const int t = tile_time(kk);
         if (big) {
-            mbar_wait(&s_full[b], (uint32_t)((kk / kStages) & 1));
+            mbar_wait(&sm.full[b], (uint32_t)((kk / kStages) & 1));
         } else {
-            for (int i = tid; i < kTile; i += blockDim.x) {
+            for (int i = tid; i < kTile; i += kChanPerBlock) {
                 const int tau = (t + i) & mask;
-                s_xz[b][i] = xz_ring[tau];
-                s_g[b][i] = g_ring[tau];
+                sm.xz[b][i] = xz_ring[tau];
+                sm.g[b][i] = g_ring[tau];
             }
-            __syncthreads();
+            __syncwarp();
         }
-        const float2* sxz = &s_xz[b][0];
-        const float* sg = &s_g[b][0];
+        const float2* sxz = &sm.xz[b][0];
+        const float* sg = &sm.g[b][0];
 
         if (kk < nE) {
             // real cascade only, zero state at tE0 (exact when tE0 == 0)
             const int cnt = min(kTile, n - t);
-            for (int i = 0; i < cnt; ++i) cascade_real(k, s, sxz[i].x);
+            for (int i = 0; i < cnt; ++i) cascade_real<FORM>(k, s, sxz[i].x);
             if (kk == nE - 1) {
-                // residuals of the zero-padded ring equation at ring positions n, n+1, in the
-                // scaled stage variables (y, q, u: stage states after sample n-1):
-                //   e0 = b1*y[n-1] + b2*y[n-2] - z_k*u[n-1] = (cy-1)*y - cq*q - z_k*u
-                //   e1 = b2*y[n-1] = cq*y
                 float e0[4], e1[4];
-                float uprev = s.up.x;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float cy = -k.ncy[i].x;
-                    e0[i] = fmaf(cy - 1.0f, s.y[i].x, -k.cq[i].x * s.q[i].x) - k.z[i].x * uprev;
-                    e1[i] = k.cq[i].x * s.y[i].x;
-                    uprev = s.y[i].x;
-                }
+                edge_residuals<FORM>(k, s, e0, e1);
                 // (t - n) odd -> e0 multiplies G[t]; even -> e1
                 const bool n_odd = (n & 1) != 0;
 #pragma unroll
@@ -356,41 +377,70 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
         } else {
             const int cnt = min(kTile, t1 - t);
             if (t < 0) {
-                run_tile<0, 0, true, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<FORM, 0, 0, true, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (t < tenv) {
-                run_tile<0, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<FORM, 0, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (t < t0) {
-                run_tile<2, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                run_tile<FORM, 2, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (full_out) {
-                if (p.lpf) run_tile<2, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else if (need_env) run_tile<1, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else run_tile<0, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                if (p.lpf) run_tile<FORM, 2, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else if (need_env) run_tile<FORM, 1, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<FORM, 0, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else {
-                if (p.lpf) run_tile<2, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else run_tile<1, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                if (p.lpf) run_tile<FORM, 2, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<FORM, 1, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             }
         }
-        __syncthreads();  // every warp is done with buffer b
+        __syncwarp();  // every lane is done with buffer b
         if (big && tid == 0 && kk + kStages < total) issue(kk + kStages);
     }
 }
 
+// One CTA = one warp: the sections' form is uniform in the CTA, so the two forms are two
+// separate straight-line programs behind one branch, and a warp that finishes early (direct
+// form: 3 FMAs per section instead of 4) frees its slot for the next work item instead of
+// waiting at a CTA barrier for slower warps (measured: DESIGN.md section 6).
+template <int MINB, int U, bool EDGE>
+__global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedParams p) {
+    static_assert(kChanPerBlock == 32, "one warp per CTA: __syncwarp is the only barrier used");
+    __shared__ __align__(128) float2 s_xz[kStages][kTile];
+    __shared__ __align__(128) float s_g[kStages][kTile];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kStages; ++b) mbar_init(&s_full[b], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const Item item = p.items[blockIdx.x];
+    const int c = item.cblock * kChanPerBlock + threadIdx.x;
+    const Smem sm{s_xz, s_g, s_full};
+    // per group of 32 channels (c_pad = C rounded up to 32): min over the group of 1 + B1 + B2
+    const float group_cy = p.chan[P_FORM * p.c_pad + c];
+#ifdef F2_SINGLE_FORM
+    (void)group_cy;
+    fused_body<F2_SINGLE_FORM, U, EDGE>(p, item, sm, c);
+#else
+    if (group_cy >= p.direct_min_cy) fused_body<1, U, EDGE>(p, item, sm, c);
+    else fused_body<0, U, EDGE>(p, item, sm, c);
+#endif
+}
+
 cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream) {
     if (n_items <= 0) return cudaSuccess;
-    // tuning knob (development only): F2_FUSED_VARIANT = "<min blocks per SM><unroll>"
+    // tuning knob (development only): F2_FUSED_VARIANT = "<min CTAs per SM><unroll>"
     static int variant = -1;
     if (variant < 0) {
         const char* v = getenv("F2_FUSED_VARIANT");
         variant = v ? atoi(v) : 0;
     }
     if (p.edge) {
-        fused_kernel<4, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        fused_kernel<16, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
         return cudaGetLastError();
     }
     switch (variant) {
-        case 58: fused_kernel<5, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 416: fused_kernel<4, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        default: fused_kernel<4, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 208: fused_kernel<20, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        case 1616: fused_kernel<16, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        default: fused_kernel<16, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
     }
     return cudaGetLastError();
 }

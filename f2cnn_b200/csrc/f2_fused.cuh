@@ -25,6 +25,7 @@ struct FusedParams {
     int w_edge;
     int w_casc;
     int w_lpf;
+    float direct_min_cy; // groups of 32 channels with min(1+B1+B2) >= this run the direct-form sections
 };
 
 cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream);

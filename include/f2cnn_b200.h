@@ -70,7 +70,9 @@ F2_API int f2_plan_get_warmup(const f2_plan* plan, int* w_imag, int* w_edge, int
  * [sum(lengths[:u]), +lengths[u]) of the flat wave buffer.  step/phase define the decimated
  * grid t = phase + j*step (InputGenerator.py:65 STEP = int(FRAMERATE*SAMPLING_PERIOD/1e6);
  * LabelDataGenerator.py:48-50 puts every timepoint on that grid).  target_items <= 0 lets
- * the library choose how finely long utterances are split into time chunks. */
+ * the library choose how finely long utterances are split into time chunks; > 0 splits them
+ * until there are about that many (utterance, 128 channels, chunk) units of work (1 = never
+ * split).  f2_batch_num_items reports CTAs: (utterance, group of 32 channels, chunk). */
 F2_API int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step, int phase, int64_t target_items,
                     f2_batch** out);
 F2_API int f2_batch_destroy(f2_batch* batch);

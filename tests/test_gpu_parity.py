@@ -313,7 +313,7 @@ def test_chunked_batch_uses_per_utterance_edge_table(gpu, oracle):
     plan = engine.plan_for(co)
     split = plan.batch(lens, target_items=4096)  # forced time chunks on a many-utterance batch
     whole = plan.batch(lens, target_items=1)   # one item per utterance, in-kernel edge pass
-    assert split.num_items > whole.num_items == 640
+    assert split.num_items > whole.num_items == 640 * 4  # one CTA per (utterance, 32 channels)
     a = split.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
     b = whole.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
     for u in (0, 319, 639):
