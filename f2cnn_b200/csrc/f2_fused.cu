@@ -8,25 +8,29 @@
 // in ONE pass over the samples, so the full-rate (C,n) matrices only reach HBM when the
 // caller asks for .GFB / .ENV1 output.
 //
-// Mapping: one CTA = one work item = (utterance, block of 128 channels, output samples
-// [t0,t1)); one thread = one channel; lanes of a warp are adjacent channels, so every
-// sample is a shared-memory broadcast and every store is a coalesced 128-byte line.
-// Tiles of 256 samples of the utterance's ring buffers (x, Im hilbert(x)) and of the
-// edge-injection kernel G are streamed into shared memory by 1-D TMA bulk copies through
-// a 4-deep mbarrier pipeline.
+// Mapping: one CTA = one warp = one work item = (utterance, group of 32 adjacent channels,
+// output samples [t0,t1)); one thread = one channel, so every sample is a shared-memory
+// broadcast and every store is a coalesced 128-byte line.  Tiles of 256 samples of the
+// utterance's ring buffers (x, Im hilbert(x)) and of the edge-injection kernel G are streamed
+// into shared memory by 1-D TMA bulk copies through a 4-deep mbarrier pipeline; 16 CTAs are
+// resident per SM.
 //
 // Arithmetic: FP32, no tensor cores (there is no contraction on this path).  The real and
 // the imaginary (Hilbert) cascades share coefficients, so they run as the two halves of
-// packed FFMA2/FADD2 instructions.  Each biquad is in "delta" form (state y[t-1] and
-// q = y[t-1]-y[t-2]), which keeps float32 coefficient quantisation harmless for poles
-// 0.039 rad from z=1:
-//     in = u[t] + z_k*u[t-1]     (+ e_k*G[t] on the imaginary half)      z_k = A1k/A0
-//     q  = cq*q + in - cy*y ;  y = y + q
+// packed FFMA2/FADD2 instructions.  Input of a section (z_k = A1k/A0):
+//     in = u[t] + z_k*u[t-1]     (+ e_k*G[t] on the imaginary half)
+// Section, per group of 32 channels (the form is uniform in a CTA):
+//   direct form  y = (in - B2*y[t-2]) - B1*y[t-1]           3 packed + 1 scalar instruction
+//   delta form   q = cq*q + in - cy*y ;  y = y + q           4 packed + 1 scalar instruction
+//                (state y[t-1] and q = y[t-1]-y[t-2]; cq = B2, cy = 1+B1+B2)
+// The delta form keeps float32 round-off and coefficient quantisation harmless for poles
+// 0.039 rad from z=1; the direct form is used where 1+B1+B2 = |1-pole|^2 is
+// large enough for it to be as accurate (FusedParams::direct_min_cy).
 // Every stage is computed WITHOUT its common numerator gain a0 = A0/gain^(1/4): stage k holds
 // y_k / a0^k, and the single factor a0^4 = A0^4/gain is applied where a value leaves the
-// kernel (folded into the low-pass b0 when the low-pass is on).  That leaves 4 packed + 1
-// scalar FMA-pipe instructions per stage: 40 FMA-pipe lane-cycles per channel-sample for
-// filterbank + envelope + low-pass, exactly the algorithmic count of SURVEY.md section 8d.
+// kernel (folded into the low-pass b0 when the low-pass is on).  In delta form that is 40
+// FMA-pipe lane-cycles per channel-sample for filterbank + envelope + low-pass, exactly the
+// algorithmic count of SURVEY.md section 8d; 32 in direct form.
 // The imaginary half solves the N2-periodic ring equation that the reference's
 // zero-padded FFT Hilbert transform implies: e_k are the residuals of the
 // zero-padded real cascade at ring positions n and n+1, G[t] is the circular Hilbert
