@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("F2CNN_B200_LIB") or os.path.join(_HERE, "libf2cnn_b20
 F2_OK = 0
 F2_I16, F2_F32, F2_F64 = 0, 1, 2
 F2_ROWS_ENVELOPE, F2_ROWS_HILBERT, F2_ROWS_LOWPASS = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class F2Error(RuntimeError):
@@ -77,6 +77,8 @@ SIGNATURES = {
     "f2_dense_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                        ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "f2_label_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "f2_event_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
     "f2_event_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "f2_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

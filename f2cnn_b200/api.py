@@ -224,3 +224,35 @@ def dense_frames(wave, coefs, LPF=False, CUTOFF=100, radius=5, step=160, normali
     if normalize and int(flag.item()) != 0:
         raise ValueError("values must all be positive")  # Training.py:18-20
     return host
+
+
+def label_fit(tracks, firsts, centers, radius=5, step=160):
+    """Slope labels for a whole corpus in one launch (LabelDataGenerator.py:60-68).
+
+    tracks[u]: float64 formant track of utterance u (Hz per 10 ms frame); firsts[u]: int array,
+    index in tracks[u] of the first of the 2*radius+1 frames of each timepoint; centers[u]: the
+    timepoints in samples.  Returns a float64 (N, 4) host array of (slope, intercept, r, p), rows in
+    utterance order then timepoint order."""
+    plan = engine.any_plan()
+    dots = 2 * int(radius) + 1
+    offs = np.concatenate([[0], np.cumsum([len(t) for t in tracks])]).astype(np.int64)
+    first_parts, center_parts = [], []
+    for u, (f, c) in enumerate(zip(firsts, centers)):
+        f = np.asarray(f, dtype=np.int64)
+        c = np.asarray(c, dtype=np.int64)
+        if f.shape != c.shape:
+            raise ValueError("firsts[%d] and centers[%d] differ in length" % (u, u))
+        if f.size and (f.min() < 0 or f.max() + dots > len(tracks[u])):
+            raise IndexError("utterance %d: a window leaves the formant track" % u)
+        first_parts.append(f + offs[u])
+        center_parts.append(c)
+    first = np.concatenate(first_parts + [np.zeros(0, np.int64)])
+    center = np.concatenate(center_parts + [np.zeros(0, np.int64)])
+    if first.size == 0:
+        return np.zeros((0, 4))
+    if center.max() > np.iinfo(np.int32).max:
+        raise OverflowError("timepoint beyond int32")
+    flat = np.concatenate([np.asarray(t, dtype=np.float64) for t in tracks])
+    out = engine.label_fit(_to_device(flat, plan.device), _to_device(first, plan.device),
+                           _to_device(center.astype(np.int32), plan.device), dots, step)
+    return _to_host(out)

@@ -14,6 +14,7 @@
 #include "../../include/f2cnn_b200.h"
 #include "f2_edge.cuh"
 #include "f2_fused.cuh"
+#include "f2_label.cuh"
 #include "f2_lanes.cuh"
 #include "f2_post.cuh"
 #include "f2_prep.cuh"
@@ -118,7 +119,7 @@ struct f2_batch {
 extern "C" {
 
 const char* f2_last_error(void) { return g_err; }
-int f2_abi_version(void) { return 3; }
+int f2_abi_version(void) { return 4; }
 
 int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1) {
     if (!b0 || !a1 || !(cutoff_hz > 0.0) || !(cutoff_hz < 8000.0))
@@ -777,6 +778,17 @@ int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int6
         return fail(F2_ERR_INVALID, "f2_dense_frames: bad arguments");
     F2_CUDA(f2::launch_dense_frames(env_t, n_channels, dots, step, i0, i1, normalize, out, out_dtype, bad_flag,
                                     (cudaStream_t)stream));
+    return F2_OK;
+}
+
+int f2_label_fit(const double* formant, const int64_t* first, const int32_t* center, int64_t n_items, int dots,
+                 int step, double* out, void* stream) {
+    if (n_items <= 0) return F2_OK;
+    if (!formant || !first || !center || !out || dots < 2 || (dots & 1) == 0 || step <= 0)
+        return fail(F2_ERR_INVALID, "f2_label_fit: bad arguments (dots must be odd and >= 3, step > 0)");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
+    F2_CUDA(f2::launch_label_fit(formant, reinterpret_cast<const long long*>(first), center, (long long)n_items, dots,
+                                 step, out, (cudaStream_t)stream));
     return F2_OK;
 }
 

@@ -7,8 +7,9 @@ install() registers this package's drop-in modules in sys.modules under the refe
 module paths:
     gammatone, gammatone.filters
     scripts.processing.GammatoneFiltering / EnvelopeExtraction / InputGenerator
+    scripts.processing.LabelDataGenerator / FBFileReader / PHNFileReader
     scripts.CNN.Evaluating   (GPU front end; model prediction and plots stay the reference's)
-Everything else under `scripts` (LabelDataGenerator, CNN, plotting, readers ...) keeps
+Everything else under `scripts` (OrganiseFiles, CNN training, plotting ...) keeps
 resolving to the reference tree, which must be importable (on sys.path) if those are used.
 Modules of the reference that were imported BEFORE install() and bound hot-path functions by
 name (`from ... import GetFilteredOutputFromArray`, Evaluating.py:19-21,
@@ -23,6 +24,9 @@ _MODULES = {
     "scripts.processing.GammatoneFiltering": "f2cnn_b200.scripts.processing.GammatoneFiltering",
     "scripts.processing.EnvelopeExtraction": "f2cnn_b200.scripts.processing.EnvelopeExtraction",
     "scripts.processing.InputGenerator": "f2cnn_b200.scripts.processing.InputGenerator",
+    "scripts.processing.FBFileReader": "f2cnn_b200.scripts.processing.FBFileReader",
+    "scripts.processing.PHNFileReader": "f2cnn_b200.scripts.processing.PHNFileReader",
+    "scripts.processing.LabelDataGenerator": "f2cnn_b200.scripts.processing.LabelDataGenerator",
     "scripts.CNN.Evaluating": "f2cnn_b200.scripts.CNN.Evaluating",
 }
 
@@ -34,13 +38,11 @@ _REBIND = {
         "GetFilteredOutputFromArray": ("scripts.processing.GammatoneFiltering", "GetFilteredOutputFromArray"),
         "filters": ("gammatone", "filters"),
     },
-    "scripts.processing.LabelDataGenerator": {
-        "GetArrayFromWAV": ("scripts.processing.GammatoneFiltering", "GetArrayFromWAV"),
-    },
     "f2cnn": {
         "FilterAllOrganisedFiles": ("scripts.processing.GammatoneFiltering", "FilterAllOrganisedFiles"),
         "ExtractAllEnvelopes": ("scripts.processing.EnvelopeExtraction", "ExtractAllEnvelopes"),
         "GenerateInputData": ("scripts.processing.InputGenerator", "GenerateInputData"),
+        "GenerateLabelData": ("scripts.processing.LabelDataGenerator", "GenerateLabelData"),
         "EvaluateOneWavFile": ("scripts.CNN.Evaluating", "EvaluateOneWavFile"),
         "EvaluateRandom": ("scripts.CNN.Evaluating", "EvaluateRandom"),
         "EvaluateWithNoise": ("scripts.CNN.Evaluating", "EvaluateWithNoise"),

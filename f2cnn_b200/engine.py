@@ -236,6 +236,20 @@ def dense_frames(env_t_dev, dots, step, i0, i1, normalize=False, out_dtype=torch
     return out, flag
 
 
+def label_fit(formant_dev, first_dev, center_dev, dots, step, stream=None):
+    """(slope, intercept, r, p) per timepoint: LabelDataGenerator.py:60-68 for every item at once.
+    formant_dev float64, first_dev int64, center_dev int32 device tensors; returns (N, 4) float64."""
+    if formant_dev.dtype != torch.float64 or first_dev.dtype != torch.int64 or center_dev.dtype != torch.int32:
+        raise TypeError("label_fit wants float64 formants, int64 first indices, int32 centers")
+    n = int(first_dev.shape[0])
+    if int(center_dev.shape[0]) != n:
+        raise ValueError("first and center differ in length")
+    out = torch.empty((n, 4), dtype=torch.float64, device=formant_dev.device)
+    check(_native.lib().f2_label_fit(_ptr(formant_dev), _ptr(first_dev), _ptr(center_dev), n, int(dots), int(step),
+                                     _ptr(out), _stream_ptr(stream)))
+    return out
+
+
 class WindowPipeline:
     """Host waves in, host (N, 2R+1, C) float32 windows out, for a whole corpus.
 

@@ -111,10 +111,10 @@ def EvaluateOneWavArray(wavArray, framerate, wavFileName, model='last_trained_mo
                         CENTER_FREQUENCIES=None, FILTERBANK_COEFFICIENTS=None):
     """One waveform through front end, CNN and figure (reference :27-113)."""
     from ... import api
-    # reference-tree pieces (labels, file readers, figure): resolved at call time
-    from scripts.processing.LabelDataGenerator import ExtractLabel
-    from scripts.processing.FBFileReader import ExtractFBFile
-    from scripts.processing.PHNFileReader import ExtractPhonemes
+    from ..processing.LabelDataGenerator import ExtractLabel
+    from ..processing.FBFileReader import ExtractFBFile
+    from ..processing.PHNFileReader import ExtractPhonemes
+    # the figure is the reference tree's (matplotlib): resolved at call time
     from scripts.plotting.PlottingCNN import PlotEnvelopesAndCNNResultsWithPhonemes
 
     cfg, st = _settings()

@@ -74,3 +74,60 @@ def corpus_waves_i16(lengths, seed=1, sigma=3000.0):
         flat[s:e] = np.clip(np.round(sigma * rng.standard_normal(e - s, dtype=np.float32)), -32768, 32767).astype(
             np.int16)
     return flat, offsets
+
+
+# ---- label-generation fixtures: VTR-style formant tracks and TIMIT-style phoneme segments -----
+_PHONES = ["iy", "ae", "s", "n", "pau", "aa", "l", "epi", "uw", "t", "er", "m", "ow", "sh", "ih", "k"]
+
+
+def formant_tracks_khz(n_frames, seed=0):
+    """(n_frames, 8) float32 in kHz (F1..F4, B1..B4), one frame per 10 ms: smooth random walks with
+    glides (clear slopes), plateaus (flat: no significant slope) and jitter, like a VTR .FB file."""
+    rng = np.random.default_rng(seed)
+    base = np.array([0.5, 1.5, 2.5, 3.5, 0.08, 0.1, 0.12, 0.15])
+    out = np.empty((n_frames, 8))
+    for col in range(8):
+        track = np.empty(n_frames)
+        v = base[col]
+        i = 0
+        while i < n_frames:
+            seg = int(rng.integers(6, 30))
+            kind = rng.integers(0, 3)
+            slope = 0.0 if kind == 0 else rng.normal(0, 0.02 * base[col])
+            for j in range(i, min(n_frames, i + seg)):
+                v = min(max(v + slope, 0.3 * base[col]), 2.0 * base[col])
+                track[j] = v
+            i += seg
+        out[:, col] = track + rng.normal(0, 0.004 * base[col], n_frames)
+    return out.astype(np.float32)
+
+
+def phoneme_segments(n_samples, seed=0):
+    """[(first sample, last sample, phoneme)] covering [0, n_samples): silence at both ends, TIMIT
+    style (segment k ends where segment k+1 starts)."""
+    rng = np.random.default_rng(seed)
+    cuts = [0, int(rng.integers(1500, 2600))]
+    while cuts[-1] < n_samples - 4000:
+        cuts.append(cuts[-1] + int(rng.integers(600, 3200)))
+    cuts.append(n_samples)
+    segs = []
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        name = "h#" if k in (0, len(cuts) - 2) else _PHONES[int(rng.integers(0, len(_PHONES)))]
+        segs.append((a, b, name))
+    return segs
+
+
+def write_fb(path, tracks_khz, samp_period=10000):
+    """VTR .FB layout: big-endian int32 nFrame, int32 sampPeriod, int16 sampSize, int16 fileType,
+    then 8 big-endian float32 per frame."""
+    import struct
+    tracks = np.asarray(tracks_khz, dtype=">f4")
+    with open(path, "wb") as f:
+        f.write(struct.pack(">iihh", tracks.shape[0], samp_period, 32, 9))
+        f.write(tracks.tobytes())
+
+
+def write_phn(path, segments):
+    with open(path, "w") as f:
+        for a, b, name in segments:
+            f.write("%d %d %s\n" % (a, b, name))

@@ -139,6 +139,18 @@ F2_API int f2_gather_windows_cn(const void* env, int dtype, int n_channels, int6
 F2_API int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int64_t i0, int64_t i1, int normalize,
                     void* out, int out_dtype, int* bad_flag, void* stream);
 
+/* ---- label generation ---------------------------------------
+ * Least-squares line through the `dots` = 2*RADIUS+1 formant frames around each timepoint and the
+ * two-sided p-value of its Pearson correlation: the body of the step loop of
+ * LabelDataGenerator.py:60-68 (numpy.linalg.lstsq + scipy.stats.pearsonr), one item per kept
+ * timepoint.  formant: device float64 track(s); first[i]: index of item i's first frame in it
+ * (FBFileReader.py:77-78: int(timepoint/wavToFormant - RADIUS)); center[i]: the timepoint in
+ * samples; abscissae are center[i] + (k - RADIUS)*step.  out: device float64 [n_items][4] =
+ * (slope a, intercept b, r, p); constant input gives r = p = NaN as scipy does.  float64
+ * arithmetic throughout (the CSV keeps round(a, 5), round(p, 5)). */
+F2_API int f2_label_fit(const double* formant, const int64_t* first, const int32_t* center, int64_t n_items, int dots,
+                        int step, double* out, void* stream);
+
 /* ---- CUDA event helpers so that a host without a CUDA binding can time on the device ----- */
 F2_API int f2_event_create(void** event);
 F2_API int f2_event_destroy(void* event);

@@ -10,6 +10,7 @@ for the 3 s cases only a fixed set of time indices (both edges + interior) is ke
 every channel, plus per-channel RMS and sums; small cases are stored whole.
 
     python oracle/make_golden.py            # rewrites tests/golden/
+    python oracle/make_golden.py --only-labels   # only tests/golden/labels.npz (section L)
 
 The reference has no tests of its own, so these fixtures are what
 pins the oracle (tests/test_oracle_golden.py) and, through it, the CUDA path.
@@ -60,11 +61,80 @@ def rms(a):
     return np.sqrt(np.mean(np.square(a), axis=-1))
 
 
+LABEL_UTTS = [("TRAIN", "DR1", "FAAA0", "SX1", 30000, 11), ("TRAIN", "DR3", "MBBB0", "SI22", 47000, 12),
+              ("TEST", "DR2", "FCCC0", "SA1", 52000, 13), ("TEST", "DR8", "MDDD0", "SX300", 39000, 14)]
+LABEL_CONF = ("[FILTERBANK]\nFRAMERATE=16000\nNCHANNELS=8\nLOW_FREQ=100\n"
+              "[CNN]\nFORMANT=2\nCENTERED=True\nRADIUS=5\nBATCH_SIZE=32\nEPOCHS=20\nRISK=0.05\n"
+              "SAMPLING_PERIOD=10000\n")
+
+
+def write_label_tree(synth, root):
+    """The synthetic resources/f2cnn tree of the label fixtures (also used by the tests)."""
+    from scipy.io import wavfile
+    made = {}
+    for (tt, dr, spk, sent, n, seed) in LABEL_UTTS:
+        d = os.path.join(root, "resources", "f2cnn", tt)
+        os.makedirs(d, exist_ok=True)
+        stem = os.path.join(d, "%s.%s.%s" % (dr, spk, sent))
+        wavfile.write(stem + ".WAV", 16000, synth.white_noise_i16(n, seed=seed))
+        tracks = synth.formant_tracks_khz(n // 160 + 3, seed=seed)
+        segs = synth.phoneme_segments(n, seed=seed)
+        synth.write_fb(stem + ".FB", tracks)
+        synth.write_phn(stem + ".PHN", segs)
+        made["%s_%s_%s_%s" % (tt, dr, spk, sent)] = (tracks, segs, n)
+    return made
+
+
+def labels_section(synth):
+    """L. LabelDataGenerator end to end (reference GenerateLabelData / ExtractLabel, files on disk)."""
+    from configparser import ConfigParser
+    from scripts.processing import LabelDataGenerator as LG
+    from scripts.processing import FBFileReader as FB
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            with open("configF2CNN.conf", "w") as f:
+                f.write(LABEL_CONF)
+            made = write_label_tree(synth, tmp)
+            LG.GenerateLabelData()
+            with open(os.path.join("trainingData", "label_data.csv")) as f:
+                csv_text = f.read()
+            cfg = ConfigParser()
+            cfg.read("configF2CNN.conf")
+            one = LG.ExtractLabel(os.path.join("resources", "f2cnn", "TEST", "DR2.FCCC0.SA1.WAV"), cfg)
+            fb_hz, _ = FB.ExtractFBFile(os.path.join("resources", "f2cnn", "TEST", "DR2.FCCC0.SA1.FB"))
+            # raw (slope, p) of EVERY grid step of one file, before the phoneme / RISK filters
+            from scipy.stats import pearsonr
+            track = fb_hz[:, 1]
+            raw = []
+            for k in range(int(52000 / 160.0 - 11 - 1)):
+                step = 800 + 160 * k
+                vals = np.array(FB.GetFromantFrequenciesAround(track, step, 5, 160.0))
+                x = np.array([step + (j - 5) * 160 for j in range(11)])
+                A = np.vstack([x, np.ones(len(x))]).T
+                [a, b], _, _, _ = np.linalg.lstsq(A, vals, rcond=None)
+                r, p = pearsonr(vals, a * x + b)
+                raw.append([step, a, b, r, p])
+        finally:
+            os.chdir(cwd)
+    d = dict(csv=np.asarray(csv_text), one_file_rows=np.asarray(repr(one)), fb_hz=fb_hz, raw=np.asarray(raw))
+    for k, (tracks, segs, n) in made.items():
+        d["tracks_" + k] = tracks
+        d["segs_" + k] = np.asarray(["%d %d %s" % s for s in segs])
+        d["n_" + k] = np.int64(n)
+    np.savez_compressed(os.path.join(OUT, "labels.npz"), **d)
+    print("labels done:", csv_text.count("\n"), "rows")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from f2cnn_b200 import synth
     filters, GF, EE, IG, TR = import_reference()
     os.makedirs(OUT, exist_ok=True)
+    if "--only-labels" in sys.argv:
+        labels_section(synth)
+        return
 
     # ---- A. coefficient design ------------------------------------------------------
     coef = {}
@@ -204,6 +274,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "inputgen.npz"), input_data=inp, csv=np.asarray(csv_text), coefs=co8,
                         **{"wave_" + k: v for k, v in waves.items()})
     print("inputgen done", inp.shape, inp.dtype)
+    labels_section(synth)
 
 
 if __name__ == "__main__":

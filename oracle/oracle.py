@@ -190,3 +190,56 @@ def utterance(wave, coefs, LPF, CUTOFF, centers=None, radius=5, step=160):
     if bad:
         raise IndexError("index out of bounds in window %d" % (bad - 1))
     return gfb, env, win
+
+
+# ---- label generation: numpy/scipy restatement --------------------
+SILENTS = ('pau', 'epi', 'h#')  # PHNFileReader.py:17
+
+
+def label_fit(values, x):
+    """LabelDataGenerator.py:62-68 for one timepoint, with the reference's own library calls:
+    (a, b) = lstsq([x, 1], values); (r, p) = pearsonr(values, a*x + b)."""
+    import warnings
+    from scipy.stats import pearsonr
+    values = np.asarray(values, dtype=np.float64)
+    x = np.asarray(x)
+    A = np.vstack([x, np.ones(len(x))]).T
+    (a, b), _, _, _ = np.linalg.lstsq(A, values, rcond=None)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r, p = pearsonr(values, a * x + b)
+    return float(a), float(b), float(r), float(p)
+
+
+def phoneme_at(segments, t):
+    """PHNFileReader.py:33-37: first (phoneme, first, last) whose closed interval holds t."""
+    for name, first, last in segments:
+        if first <= t <= last:
+            return name
+    return 'h#'
+
+
+def extract_label(track_hz, segments, n_samples, ident, framerate=16000, radius=5, risk=0.05, period=10000):
+    """LabelDataGenerator.py:22-77 from in-memory inputs: track_hz = the chosen formant column in
+    Hz, segments = [(phoneme, first, last)], ident = [TEST|TRAIN, region, speaker, sentence]."""
+    dots = 2 * radius + 1
+    to_formant = framerate * period * (1.0 / 1000000)
+    nb = int(n_samples / to_formant - dots - 1)
+    step = int(to_formant)
+    start = int(step * radius)
+    rows = []
+    for k in range(nb):
+        t = start + k * step
+        name = phoneme_at(segments, t)
+        if name in SILENTS:
+            continue
+        if not name:
+            break
+        lo, hi = int(t / to_formant - radius), int(t / to_formant + radius) + 1  # FBFileReader.py:77-78
+        if lo < 0 or hi >= len(track_hz):
+            raise IndexError("window outside the formant track")  # the reference prints and exits
+        x = np.array([t + (j - radius) * step for j in range(dots)])
+        a, _, _, p = label_fit(track_hz[lo:hi], x)
+        if p < risk:
+            rows.append(list(ident) + [name, t, round(a, 5), round(p, 5), 1 if a > 0 else 0])
+    return rows or None

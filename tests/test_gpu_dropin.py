@@ -29,6 +29,8 @@ def tree(tmp_path, monkeypatch):
         d.mkdir(parents=True, exist_ok=True)
         w = synth.speech_like_i16(n, seed=n)
         wavfile.write(str(d / (name + ".WAV")), 16000, w)
+        synth.write_fb(str(d / (name + ".FB")), synth.formant_tracks_khz(n // 160 + 3, seed=n))
+        synth.write_phn(str(d / (name + ".PHN")), synth.phoneme_segments(n, seed=n))
         waves[(tt, name)] = w
     return tmp_path, waves
 
@@ -151,32 +153,33 @@ def test_evaluating_front_end_and_driver(tree, oracle, monkeypatch):
         keras.models = types.SimpleNamespace(load_model=lambda name: _Net())
         keras.backend = types.SimpleNamespace(clear_session=lambda: None)
         monkeypatch.setitem(sys.modules, "keras", keras)
-        stubs = {
-            "scripts.processing.LabelDataGenerator": dict(ExtractLabel=lambda name, c: [[0, 0, 0, 0, 0, 1000, 0, 0, 1],
-                                                                                       [0, 0, 0, 0, 0, 1200, 0, 0, 0]]),
-            "scripts.processing.FBFileReader": dict(ExtractFBFile=lambda name: (np.zeros((3, 4)), 100)),
-            "scripts.processing.PHNFileReader": dict(ExtractPhonemes=lambda name: [("aa", 0, 10)]),
-            "scripts.plotting": {},
-            "scripts.plotting.PlottingCNN": dict(PlotEnvelopesAndCNNResultsWithPhonemes=lambda *a: seen.update(plot=a)),
-        }
-        for name, attrs in stubs.items():
+        for name, attrs in {"scripts.plotting": {}, "scripts.plotting.PlottingCNN": dict(
+                PlotEnvelopesAndCNNResultsWithPhonemes=lambda *a: seen.update(plot=a))}.items():
             m = types.ModuleType(name)
             m.__dict__.update(attrs)
             if not attrs:
                 m.__path__ = []
             monkeypatch.setitem(sys.modules, name, m)
-        Evaluating.EvaluateOneWavArray(w, 16000, "x.WAV", LPF=True, CUTOFF=50)
+        wav = os.path.join("resources", "f2cnn", "TEST", "DR1.SPK2.SI3.WAV")
+        Evaluating.EvaluateOneWavArray(w, 16000, wav, LPF=True, CUTOFF=50)
         assert seen["x"].shape == (frames.shape[0], 11, 32, 1) and np.array_equal(seen["x"][..., 0], frames)
-        envs, scores, acc, cf = seen["plot"][:4]
+        envs, scores, acc, cf, phonemes, formants = seen["plot"][:6]
         assert envs.shape == (32, len(w)) and rel(envs, eo) <= TOL and scores.shape == (frames.shape[0], 2)
-        # scores cross at the middle frame: decisions 0 before it; frames 1001..1159 -> label 1 (misses),
-        # 1041..1199 -> nearer label decides; just check against the restated rule
+        # labels, phonemes and formants come from the .FB / .PHN files next to the WAV
+        from f2cnn_b200 import synth
+        segs = [(name, a, b) for a, b, name in synth.phoneme_segments(len(w), seed=len(w))]
+        track = np.round(synth.formant_tracks_khz(len(w) // 160 + 3, seed=len(w)).astype(np.float64) * 1000, 2)
+        assert phonemes == segs and np.array_equal(formants, track)
+        rows = oracle.extract_label(track[:, 1], segs, len(w), ["TEST", "DR1", "SPK2", "SI3"])
+        assert rows, "fixture should give at least one label"
+        labels = [(r[-4], r[-1]) for r in rows]
         dec = [int(s[1] > s[0]) for s in scores]
         good = n = 0
         for t, d in enumerate(dec):
-            if 1000 < t < 1200 and min(t - 1000, 1200 - t) < 160:
-                n += 1
-                good += int(d == (1 if t - 1000 <= 1200 - t else 0))
-        assert acc == good / n
+            for (b, cb), (a, ca) in zip(labels[:-1], labels[1:]):
+                if b < t < a and min(t - b, a - t) < 160:
+                    n += 1
+                    good += int(d == (cb if t - b <= a - t else ca))
+        assert n > 0 and acc == good / n
     finally:
         dropin.uninstall()

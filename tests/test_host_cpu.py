@@ -137,7 +137,15 @@ def test_dropin_install_registers_reference_module_paths():
             assert callable(getattr(EnvelopeExtraction, name))
         for name in ("GetListOfEnvelopeFilesAndTimepoints", "GenerateInputData"):
             assert callable(getattr(InputGenerator, name))
-        assert len(mods) == 6
+        assert len(mods) == 9
+        from scripts.processing import FBFileReader, LabelDataGenerator, PHNFileReader
+        for mod, names in ((LabelDataGenerator, ("ExtractLabel", "GenerateLabelData")),
+                           (FBFileReader, ("ExtractFBFile", "GetFormantFrequencies", "GetFromantFrequenciesAround")),
+                           (PHNFileReader, ("ExtractPhonemes", "GetPhonemeFromArrayAt", "GetPhonemeAt"))):
+            assert mod.__name__.startswith("f2cnn_b200.")
+            for name in names:
+                assert callable(getattr(mod, name))
+        assert PHNFileReader.SILENTS == ['pau', 'epi', 'h#']
         from scripts.CNN import Evaluating
         for name in ("EvaluateOneWavArray", "EvaluateOneWavFile", "EvaluateRandom", "EvaluateWithNoise", "RMS",
                      "SNRdbToSNRlinear"):

@@ -75,4 +75,21 @@ for tag, kw, bytes_per_cs in (("env_t_f32_time_major", dict(env_t=True), 4.04),
     out["fullrate_" + tag] = {"device_ms": ms, "channel_samples_per_s": cs / ms * 1e3,
                               "algorithmic_GBps": bytes_per_cs * cs / ms / 1e6}
     del res
+# ---- label generation: the corpus label grid, one launch ----
+lens = synth.corpus_lengths(4620, seed=1)
+rng = np.random.default_rng(5)
+tracks = [1500.0 + np.cumsum(rng.normal(0, 8.0, int(n) // 160 + 3)) for n in lens]
+centers = [synth.label_grid(int(n)) for n in lens]
+firsts = [c // 160 - 5 for c in centers]
+offs = np.concatenate([[0], np.cumsum([len(t) for t in tracks])]).astype(np.int64)
+first_d = torch.from_numpy(np.concatenate([f + o for f, o in zip(firsts, offs)])).cuda()
+center_d = torch.from_numpy(np.concatenate(centers).astype(np.int32)).cuda()
+flat_d = torch.from_numpy(np.concatenate(tracks)).cuda()
+ms = timed(lambda: engine.label_fit(flat_d, first_d, center_d, 11, 160), reps=10)
+t = time.perf_counter()
+fit = api.label_fit(tracks, firsts, centers)
+host_ms = (time.perf_counter() - t) * 1e3
+out["label_fit_corpus_grid"] = {"timepoints": int(first_d.shape[0]), "device_ms": ms, "api_host_ms_incl_copies": host_ms,
+                                "note": "reference: numpy.linalg.lstsq + scipy.stats.pearsonr per timepoint, "
+                                        "~0.16 s per file (SURVEY.md 8f)"}
 print(json.dumps(out, indent=1))
