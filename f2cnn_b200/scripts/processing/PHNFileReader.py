@@ -7,14 +7,14 @@ and 'h#' when none does (:33-37).  phoneme_at() is the same lookup for an array 
 """
 import numpy
 
-STOPS = ['b', 'd', 'g', 'p', 't', 'k', 'dx', 'q']
-AFFRICATIVES = ['jh', 'ch']
-FRICATIVES = ['s', 'sh', 'w', 'wh', 'f', 'th', 'v', 'dh']
-NASALS = ['m', 'n', 'ng', 'em', 'en', 'eng', 'nx']
-SEMIVOWELS_AND_GLIDES = ['l', 'r', 'w', 'y', 'hh', 'hv', 'el']
-VOWELS = ["iy", "ih", "eh", "ey", "ae", "aa", "aw", "ay", "ah", "ao",
-          "oy", "ow", "uh", "uw", "ux", "er", "ax", "ix", "axr", "ax-h"]
-SILENTS = ['pau', 'epi', 'h#']
+# TIMIT phone classes, same members and order as the reference's lists (:10-17)
+STOPS = 'b d g p t k dx q'.split()
+AFFRICATIVES = 'jh ch'.split()
+FRICATIVES = 's sh w wh f th v dh'.split()
+NASALS = 'm n ng em en eng nx'.split()
+SEMIVOWELS_AND_GLIDES = 'l r w y hh hv el'.split()
+VOWELS = 'iy ih eh ey ae aa aw ay ah ao oy ow uh uw ux er ax ix axr ax-h'.split()
+SILENTS = 'pau epi h#'.split()
 
 
 def ExtractPhonemes(phnFilename):
