@@ -53,6 +53,7 @@ struct Coef {
     float2 z[4];    // A1k/A0 (the stage's zero), broadcast to both halves
     float2 cq[4];
     float2 ncy[4];
+    float2 zn[3];   // direct form only: z[i+1] - B1 of section i (next section's input from this one's state)
     float g4;       // A0^4/gain: the cascade's output scale
 };
 
@@ -60,8 +61,8 @@ struct State {
     float2 y[4];
     float2 q[4];
     float2 up;    // previous stage-1 input (x[t-1], xi[t-1])
-    float l;      // low-pass state, scaled by 1/b0
-    float eprev;  // previous envelope sample
+    float l;      // one-pole low-pass state w[t] = k*w[t-1] + |y[t]|
+    float wprev;  // w[t-1] (the low-pass output is b0*(w[t] + w[t-1]))
 };
 
 __device__ __forceinline__ void reset(State& s) {
@@ -72,7 +73,7 @@ __device__ __forceinline__ void reset(State& s) {
     }
     s.up = make_float2(0.f, 0.f);
     s.l = 0.f;
-    s.eprev = 0.f;
+    s.wprev = 0.f;
 }
 
 // One sample through the packed (real, imag) 4-stage cascade.  e[] = injection
@@ -81,30 +82,43 @@ template <int FORM>
 __device__ __forceinline__ float2 cascade(const Coef& k, State& s, float2 u, float g, const float (&e)[4]) {
     float2 up = s.up;
     s.up = u;
+    if (FORM == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2 in = __ffma2_rn(k.z[i], up, u);
-        in.y = fmaf(e[i], g, in.y);
-        const float2 yo = s.y[i];
-        float2 yn;
-        if (FORM == 0) {
+        for (int i = 0; i < 4; ++i) {
+            float2 in = __ffma2_rn(k.z[i], up, u);
+            in.y = fmaf(e[i], g, in.y);
+            const float2 yo = s.y[i];
             float2 qn = __ffma2_rn(k.cq[i], s.q[i], in);
             qn = __ffma2_rn(k.ncy[i], yo, qn);
-            yn = __fadd2_rn(yo, qn);
+            const float2 yn = __fadd2_rn(yo, qn);
             s.q[i] = qn;
-        } else {
-            const float2 acc = __ffma2_rn(k.cq[i], s.q[i], in);  // in - B2*y[t-2]
-            yn = __ffma2_rn(k.ncy[i], yo, acc);                  //    - B1*y[t-1]
-            s.q[i] = yo;
+            s.y[i] = yn;
+            up = yo;
+            u = yn;
         }
-        s.y[i] = yn;
-        up = yo;
-        u = yn;
+        return u;
     }
-    return u;
+    // Direct form.  With acc = in - B2*y[t-2], the section output is y = acc - B1*y[t-1] and the
+    // NEXT section's input is z'*y[t-1] + y = acc + (z' - B1)*y[t-1]: both read (y[t-1], acc), so
+    // the second issues right behind the first without waiting for y (k.zn = z' - B1).
+    float2 in = __ffma2_rn(k.z[0], up, u);
+    in.y = fmaf(e[0], g, in.y);
+    float2 yn;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 yo = s.y[i];
+        const float2 acc = __ffma2_rn(k.cq[i], s.q[i], in);
+        yn = __ffma2_rn(k.ncy[i], yo, acc);
+        if (i < 3) {
+            in = __ffma2_rn(k.zn[i], yo, acc);
+            in.y = fmaf(e[i + 1], g, in.y);
+        }
+        s.q[i] = yo;
+        s.y[i] = yn;
+    }
+    return yn;
 }
 
-// Real half only (scalar), used for the edge-residual pass.
 template <int FORM>
 __device__ __forceinline__ void cascade_real(const Coef& k, State& s, float u) {
     float up = s.up.x;
@@ -163,15 +177,16 @@ struct OutCtx {
     float env_scale;  // g4 (no low-pass) or g4*b0 (low-pass): applied when a value is stored
 };
 
-// Unscaled envelope sample: |y| (ENV 1) or the low-pass state (ENV 2); the caller multiplies
-// by OutCtx::env_scale only for the samples that are actually stored.
+// Unscaled envelope sample.  ENV 1: |y|.  ENV 2: the one-pole state w[t] = k*w[t-1] + |y[t]|; the
+// butter(1) low-pass output is b0*(w[t] + w[t-1]) (same transfer function (1+z^-1)/(1-k*z^-1) as
+// the reference's lfilter, EnvelopeExtraction.py:47-48), and that sum is only formed for the
+// samples that are stored -- one FMA per sample instead of an add and an FMA.
 template <int ENV>
 __device__ __forceinline__ float envelope(const FusedParams& p, State& s, float2 y) {
     float e = fast_sqrt(fmaf(y.x, y.x, y.y * y.y));
     if (ENV == 2) {
-        s.l = fmaf(p.lp_k, s.l, e + s.eprev);
-        s.eprev = e;
-        e = s.l;
+        e = fmaf(p.lp_k, s.l, e);
+        s.l = e;
     }
     return e;
 }
@@ -201,6 +216,7 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             gv[4 * j + 3] = v.w;
         }
         float ev[U];
+        const float wprev = s.wprev;  // ENV 2: w of the sample before this block
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const float2 u = make_float2(ZEROX ? 0.f : xv[2 * j], xv[2 * j + 1]);
@@ -208,9 +224,13 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             if (ENV > 0) ev[j] = envelope<ENV>(p, s, y);
             if (OUT == 2) {
                 if (o.gfb && active) __stcs(o.gfb + (size_t)j * o.C, k.g4 * y.x);
-                if (ENV > 0 && o.env && active) __stcs(o.env + (size_t)j * o.C, o.env_scale * ev[j]);
+                if (ENV > 0 && o.env && active) {
+                    const float v = ENV == 2 ? ev[j] + (j > 0 ? ev[j > 0 ? j - 1 : 0] : wprev) : ev[j];
+                    __stcs(o.env + (size_t)j * o.C, o.env_scale * v);
+                }
             }
         }
+        if (ENV == 2) s.wprev = ev[U - 1];
         if (OUT == 2) {
             if (o.gfb) o.gfb += U * o.C;
             if (o.env) o.env += U * o.C;
@@ -219,8 +239,13 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             while (o.next_dec < t + i + U) {
                 const int r = o.next_dec - (t + i);
                 float v = ev[0];
+                float vp = wprev;
 #pragma unroll
-                for (int j = 1; j < U; ++j) v = (r == j) ? ev[j] : v;
+                for (int j = 1; j < U; ++j) {
+                    v = (r == j) ? ev[j] : v;
+                    if (ENV == 2) vp = (r == j) ? ev[j - 1] : vp;
+                }
+                if (ENV == 2) v += vp;
                 if (active) __stcs(o.dec, o.env_scale * v);
                 o.dec += o.C;
                 o.next_dec += o.step;
@@ -233,18 +258,20 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
         const float2 y = (i & 1) ? cascade<FORM>(k, s, u, sg[i], eo) : cascade<FORM>(k, s, u, sg[i], ee);
         float e = 0.f;
         if (ENV > 0) e = envelope<ENV>(p, s, y);
+        const float out = ENV == 2 ? e + s.wprev : e;
+        if (ENV == 2) s.wprev = e;
         if (OUT == 2) {
             if (o.gfb) {
                 if (active) __stcs(o.gfb, k.g4 * y.x);
                 o.gfb += o.C;
             }
             if (ENV > 0 && o.env) {
-                if (active) __stcs(o.env, o.env_scale * e);
+                if (active) __stcs(o.env, o.env_scale * out);
                 o.env += o.C;
             }
         }
         if (OUT > 0 && ENV > 0 && o.dec && o.next_dec == t + i) {
-            if (active) __stcs(o.dec, o.env_scale * e);
+            if (active) __stcs(o.dec, o.env_scale * out);
             o.dec += o.C;
             o.next_dec += o.step;
         }
@@ -283,6 +310,11 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
             k.z[i] = make_float2(z, z);
             k.cq[i] = make_float2(cq, cq);
             k.ncy[i] = make_float2(ncy, ncy);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float zn = FORM == 1 ? k.z[i + 1].x + k.ncy[i].x : 0.f;
+            k.zn[i] = make_float2(zn, zn);
         }
     }
 
@@ -387,9 +419,11 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
             } else if (t < t0) {
                 run_tile<FORM, 2, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (full_out) {
-                if (p.lpf) run_tile<FORM, 2, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else if (need_env) run_tile<FORM, 1, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else run_tile<FORM, 0, 2, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                // full-rate stores: the 8-sample unroll is the faster one (3.9 vs 4.9 ms on 256 utterances)
+                constexpr int UF = U < 8 ? U : 8;
+                if (p.lpf) run_tile<FORM, 2, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else if (need_env) run_tile<FORM, 1, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<FORM, 0, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else {
                 if (p.lpf) run_tile<FORM, 2, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else run_tile<FORM, 1, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
@@ -438,13 +472,14 @@ cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream)
         variant = v ? atoi(v) : 0;
     }
     if (p.edge) {
-        fused_kernel<16, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        if (variant == 168) fused_kernel<16, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        else fused_kernel<16, 16, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
         return cudaGetLastError();
     }
     switch (variant) {
+        case 168: fused_kernel<16, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
         case 208: fused_kernel<20, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 1616: fused_kernel<16, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        default: fused_kernel<16, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+        default: fused_kernel<16, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
     }
     return cudaGetLastError();
 }

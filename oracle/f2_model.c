@@ -62,17 +62,20 @@ static void prep(const double *k10, chan_t *p)
 static inline float cascade_step(const chan_t *p, float *y, float *q, float u, float up, const float *inj, int form)
 {
     if (form == 1) {
-        /* direct form I: y[k] = y[t-1], q[k] = y[t-2]; 3 FMAs per stage */
+        /* direct form: y[k] = y[t-1], q[k] = y[t-2]; acc = in - B2*y[t-2]; y = acc - B1*y[t-1]; the next
+         * section's input is formed from the same (y[t-1], acc): in' = acc + (z' - B1)*y[t-1] */
+        float in = fmaf(p->z[0], up, u);
+        if (inj) in = in + inj[0];
         for (int k = 0; k < 4; ++k) {
-            float in = fmaf(p->z[k], up, u);
-            if (inj) in = in + inj[k];
             float yp = y[k];
-            float t = fmaf(p->nb2[k], q[k], in);
-            float yn = fmaf(p->nb1[k], yp, t);
+            float acc = fmaf(p->nb2[k], q[k], in);
+            float yn = fmaf(p->nb1[k], yp, acc);
+            if (k < 3) {
+                in = fmaf(p->z[k + 1] + p->nb1[k], yp, acc);
+                if (inj) in = in + inj[k + 1];
+            }
             q[k] = yp;
             y[k] = yn;
-            up = yp;
-            u = yn;
         }
         return y[3];
     }
@@ -148,7 +151,7 @@ void f2m_run(const float *xf, const float *xi, const float *G, int64_t n, int64_
         /* main pass */
         for (int k = 0; k < 4; ++k) { y[k] = 0; q[k] = 0; }
         up = 0.0f;
-        float l = 0.0f, eprev = 0.0f;
+        float w = 0.0f, wprev = 0.0f;
         for (int64_t t = 0; t < n; ++t) {
             float yr = cascade_step(&p, y, q, xf[t], up, NULL, form);
             up = xf[t];
@@ -163,10 +166,10 @@ void f2m_run(const float *xf, const float *xi, const float *G, int64_t n, int64_
             if (out_env) {
                 float e = sqrtf(fmaf(yr, yr, yi * yi));
                 if (lpf) {
-                    /* l~ = (e + eprev) + k*l~ ; out = b0*l~ */
-                    l = fmaf(k_lp, l, e + eprev);
-                    eprev = e;
-                    out_env[(size_t)c * n + t] = (p.g4 * b0_lp) * l;
+                    /* one-pole state w = e + k*w ; out = b0*(w[t] + w[t-1]) */
+                    w = fmaf(k_lp, w, e);
+                    out_env[(size_t)c * n + t] = (p.g4 * b0_lp) * (w + wprev);
+                    wprev = w;
                 } else out_env[(size_t)c * n + t] = p.g4 * e;
             }
         }
