@@ -1,6 +1,8 @@
 #!/bin/bash
-# Development helper: time the fused kernel for each compiled (min-blocks, unroll) variant.
-for v in 0 58 68 44 54 64 416 316; do
+# Development helper: time the fused kernel for each compiled variant of launch_fused
+# (F2_FUSED_VARIANT: 0 = default <16 CTAs/SM, unroll 16>, 168 = <16, 8>, 208 = <20, 8>).
+# profiles/r01b_tune_variants.log was made with the 128-thread kernel's variants of that time.
+for v in 0 168 208; do
   F2_FUSED_VARIANT=$v python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
