@@ -145,7 +145,16 @@ def cpu_arm(coefs, lengths, seed, seconds, steps=1, warmup=0):
         step_rates.append(C * sn / st)
         total_t += st
         total_n += sn
+    # single-core figure beside it: two utterances on one thread
+    orc.set_num_threads(1)
+    t1, n1 = 0.0, 0
+    for k in range(2):
+        d, n = run(order[(pos + k) % len(order)])
+        t1 += d
+        n1 += n
+    orc.set_num_threads(avail)
     return {"value": C * total_n / total_t, "unit": "channel-samples/s", "cores": cores, "kind": "port",
+            "value_single_core": C * n1 / t1,
             "sample": "%d utterances (%d samples) of the corpus per step x %d steps, float64 C port of the "
                       "reference algorithm, OpenMP over channels, in memory" % (per_step, total_n // max(steps, 1),
                                                                                 steps),
