@@ -189,8 +189,12 @@ int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** ou
     p->C = C;
     p->c_pad = c_pad;
     p->min_neg_log_r = min_nlr;
-    // truncated-history lengths: r^W * W^3 envelope of the 4-section cascade below float32
-    // resolution (measured against the float64 oracle: 21.5/-ln r -> 1e-9, 29/-ln r -> 1e-12)
+    // truncated-history lengths.  The cascade's impulse response decays like t^3 r^t, so for an
+    // input that adds up coherently (a tone on the slowest channel's centre) the part of the steady
+    // state older than W samples is Gamma(4, -W ln r)/6 of the whole: 7e-7 at 21.5/-ln r (w_imag),
+    // 2e-9 at 29/-ln r (w_edge, w_casc) -- below float32 resolution.  On broadband input the error is
+    // flat down to 18/-ln r (tools/warmup_sweep.py), but that would leave 1.5e-5 in the coherent
+    // case (and 4e-3 on a 3-sample input, whose 4-sample ring is nothing but coherent) for a 1 % gain.
     p->w_imag = round_up_tile(21.5 / min_nlr);
     p->w_edge = round_up_tile(29.0 / min_nlr);
     p->w_casc = p->w_edge;

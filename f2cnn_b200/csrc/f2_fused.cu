@@ -143,6 +143,39 @@ __device__ __forceinline__ void cascade_real(const Coef& k, State& s, float u) {
     }
 }
 
+// Imaginary half only (scalar): the periodic warm-up before t = 0, where the real half is
+// identically zero -- 16 scalar FMAs per sample instead of 12-16 packed instructions.
+template <int FORM>
+__device__ __forceinline__ void cascade_imag(const Coef& k, State& s, float u, float g, const float (&e)[4]) {
+    float up = s.up.y;
+    s.up.y = u;
+    if (FORM == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float in = fmaf(e[i], g, fmaf(k.z[i].x, up, u));
+            const float yo = s.y[i].y;
+            float qn = fmaf(k.cq[i].x, s.q[i].y, in);
+            qn = fmaf(k.ncy[i].x, yo, qn);
+            const float yn = yo + qn;
+            s.q[i].y = qn;
+            s.y[i].y = yn;
+            up = yo;
+            u = yn;
+        }
+    } else {
+        float in = fmaf(e[0], g, fmaf(k.z[0].x, up, u));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float yo = s.y[i].y;
+            const float acc = fmaf(k.cq[i].x, s.q[i].y, in);
+            const float yn = fmaf(k.ncy[i].x, yo, acc);
+            if (i < 3) in = fmaf(e[i + 1], g, fmaf(k.zn[i].x, yo, acc));
+            s.q[i].y = yo;
+            s.y[i].y = yn;
+        }
+    }
+}
+
 // Residuals of the zero-padded ring equation at ring positions n and n+1, from the stage states
 // after sample n-1 (y = y[n-1]; u = the stage's input at n-1), in the scaled stage variables:
 //   e0 = b1*y[n-1] + b2*y[n-2] - z_k*u[n-1]      e1 = b2*y[n-1]
@@ -413,7 +446,14 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
         } else {
             const int cnt = min(kTile, t1 - t);
             if (t < 0) {
-                run_tile<FORM, 0, 0, true, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                // periodic warm-up of the imaginary path (t is a multiple of kTile: parity of t+i = parity of i)
+#pragma unroll 2
+                for (int i = 0; i < cnt; i += 2) {
+                    const float4 xz2 = *reinterpret_cast<const float4*>(sxz + i);
+                    const float2 g2 = *reinterpret_cast<const float2*>(sg + i);
+                    cascade_imag<FORM>(k, s, xz2.y, g2.x, ee);
+                    cascade_imag<FORM>(k, s, xz2.w, g2.y, eo);
+                }
             } else if (t < tenv) {
                 run_tile<FORM, 0, 0, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (t < t0) {
