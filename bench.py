@@ -306,10 +306,10 @@ def main():
     roofline = {"bound": "fp32_fma", "kernel": "fused_kernel", "achieved": achieved, "peak": fma_peak,
                 "unit": "TFLOP/s", "frac": achieved / fma_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one fused_kernel launch on this workload,
-                # ncu --set full capture summarised in profiles/r01m_ncu_final.md (algorithmic: 3.37e9;
-                # the one-warp CTAs of an utterance drift apart in time and re-read ~50 % of the ring tiles
-                # that have left L2 -- 1.5 % of HBM peak, the kernel is FMA-bound)
-                "traffic": 5.113e9 if args.utts == N_UTTS else None,
+                # ncu --set full capture summarised in profiles/r01o_ncu_final.md (algorithmic: 3.37e9;
+                # the one-warp CTAs of an utterance drift apart in time and re-read ~65 % of the ring tiles
+                # that have left L2 -- 1.7 % of HBM peak, the kernel is FMA-bound)
+                "traffic": 5.523e9 if args.utts == N_UTTS else None,
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 entry); "
                                "tools/fma_peak.cu measured 73.8 TFLOP/s sustained (FFMA2) on this pool",
                 "kernel_ms": fused_ms, "kernel_share_of_step": fused_ms / ms_step,
