@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 FS, C, LOW, CUTOFF, RADIUS, STEP = 16000, 128, 100, 50, 5, 160
 N_UTTS, LEN_LO, LEN_HI = 4620, 32000, 64000
 FLOP_PER_CS = 80.0  # 40 FP32 FMA per channel-sample: filterbank + envelope + LPF
-KERNELS_PER_STEP = 7  # fft cols/rows fwd, hilbert mask (+G table), fft cols/rows inv, fused, gather
+KERNELS_PER_STEP = 6  # fft cols/rows fwd, hilbert mask (+G table), fft cols/rows inv, fused (stores the windows)
 
 
 def parse():
@@ -217,9 +217,20 @@ def main():
     windows = torch.empty((n_windows, dots, C), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()
 
+    grid_offsets, grid_rows = batch.grid_windows(dots)
+    assert grid_rows == n_windows
+
     def step(events=None):
-        batch.run(wave_dev, lpf=True, cutoff=CUTOFF, out={"dec": dec}, fused_events=events)
-        engine.gather_windows(dec, base_dev, dots, 1, out=windows)
+        # the label-grid windows are stored by the fused kernel itself (no decimated round trip)
+        batch.run(wave_dev, lpf=True, cutoff=CUTOFF, windows=(grid_offsets, dots, windows), fused_events=events)
+
+    # the fused window store must equal decimated frames + gather (the general path), bit for bit
+    step()
+    batch.run(wave_dev, lpf=True, cutoff=CUTOFF, out={"dec": dec})
+    check = torch.empty((min(n_windows, 4096), dots, C), dtype=torch.float32, device=dev)
+    for r0 in (0, max(n_windows // 2 - 2048, 0), max(n_windows - 4096, 0)):
+        engine.gather_windows(dec, base_dev[r0:r0 + check.shape[0]], dots, 1, out=check[:min(4096, n_windows - r0)])
+        assert torch.equal(check[:min(4096, n_windows - r0)], windows[r0:r0 + 4096]), "window store differs from gather"
 
     def barrier():
         torch.cuda.synchronize()

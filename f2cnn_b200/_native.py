@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("F2CNN_B200_LIB") or os.path.join(_HERE, "libf2cnn_b20
 F2_OK = 0
 F2_I16, F2_F32, F2_F64 = 0, 1, 2
 F2_ROWS_ENVELOPE, F2_ROWS_HILBERT, F2_ROWS_LOWPASS = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class F2Error(RuntimeError):
@@ -35,6 +35,9 @@ class RunArgs(ctypes.Structure):
         ("dec", ctypes.c_void_p),
         ("ev_fused_start", ctypes.c_void_p),
         ("ev_fused_stop", ctypes.c_void_p),
+        ("windows", ctypes.c_void_p),
+        ("win_offsets", ctypes.c_void_p),
+        ("win_dots", ctypes.c_int),
     ]
 
 

@@ -119,7 +119,7 @@ struct f2_batch {
 extern "C" {
 
 const char* f2_last_error(void) { return g_err; }
-int f2_abi_version(void) { return 4; }
+int f2_abi_version(void) { return 5; }
 
 int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1) {
     if (!b0 || !a1 || !(cutoff_hz > 0.0) || !(cutoff_hz < 8000.0))
@@ -468,6 +468,12 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     if ((a->gfb && a->gfb_dtype != F2_F32 && a->gfb_dtype != F2_F64) ||
         (a->env && a->env_dtype != F2_F32 && a->env_dtype != F2_F64))
         return fail(F2_ERR_INVALID, "f2_batch_run: output dtype must be F2_F32 or F2_F64");
+    if (a->windows) {
+        if (a->gfb || a->env || a->env_t || a->dec)
+            return fail(F2_ERR_INVALID, "f2_batch_run: `windows` is a stand-alone output mode (no gfb/env/env_t/dec)");
+        if (!a->win_offsets || a->win_dots < 1)
+            return fail(F2_ERR_INVALID, "f2_batch_run: `windows` needs win_offsets and win_dots >= 1");
+    }
     const bool want_gfb = a->gfb != nullptr;
     const bool want_env_scratch = a->env != nullptr && a->env_t == nullptr;
     const size_t need = f2_batch_workspace_bytes(b, want_gfb, want_env_scratch);
@@ -501,7 +507,7 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
         env_t = (float*)cur;
         cur += ws_full_bytes(b);
     }
-    const bool need_env = env_t != nullptr || a->dec != nullptr;
+    const bool need_env = env_t != nullptr || a->dec != nullptr || a->windows != nullptr;
 
     f2::PrepParams pp;
     pp.utts = b->d_utts;
@@ -582,6 +588,9 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     fp.gfb_t = gfb_t;
     fp.env_t = env_t;
     fp.dec = a->dec;
+    fp.win = a->windows;
+    fp.win_off = reinterpret_cast<const long long*>(a->win_offsets);
+    fp.win_dots = a->win_dots;
     fp.edge = nullptr;
     if (need_env && b->n_items > b->n_whole) {
         // time-chunked batch: the edge residuals are per utterance, compute them once instead of

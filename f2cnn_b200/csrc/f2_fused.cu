@@ -199,16 +199,40 @@ __device__ __forceinline__ void edge_residuals(const Coef& k, const State& s, fl
 
 // ENV: 0 = cascade only, 1 = magnitude, 2 = magnitude + low-pass.
 // OUT: 0 = nothing leaves the kernel (warm-up), 1 = decimated frames only, 2 = full-rate
-//      time-major stores (and decimated frames when asked).
+//      time-major stores (and decimated frames when asked), 3 = every decimated frame goes
+//      straight into the (up to win_dots) window rows that contain it.
 struct OutCtx {
     float* gfb;     // points at sample t of this thread's channel (or null)
     float* env;
-    float* dec;     // points at the next decimated frame of this channel (or null)
+    float* dec;     // OUT 1/2: the next decimated frame of this channel (or null).  OUT 3: slot 0 of the
+                    // window that STARTS at the next decimated frame
     int next_dec;   // time index of the next decimated frame
     int step;
     size_t C;
     float env_scale;  // g4 (no low-pass) or g4*b0 (low-pass): applied when a value is stored
+    int wk;         // OUT 3: index (within the utterance) of the next decimated frame
+    int nwin;       // OUT 3: windows of this utterance
 };
+
+// OUT 3: decimated frame j = o.wk with value v goes to slot s of window j-s, s < dots, where that
+// window exists: ((row0 + j - s)*dots + s)*C = (row0 + j)*dots*C - s*(dots-1)*C.  dots and C are
+// read from the kernel parameters so that the per-slot offsets stay on the uniform datapath.
+__device__ __forceinline__ void store_window_entries(const FusedParams& p, OutCtx& o, float v, bool active) {
+    const int dots = p.win_dots;
+    const long long back = (long long)(dots - 1) * (long long)p.C;
+    float* wp = o.dec;
+    if (o.wk >= dots - 1 && o.wk < o.nwin) {  // interior frame: all `dots` windows exist
+        if (active)
+            for (int s = 0; s < dots; ++s) __stcs(wp - (long long)s * back, v);
+    } else {
+        for (int s = 0; s < dots; ++s) {
+            const int k = o.wk - s;
+            if (k >= 0 && k < o.nwin && active) __stcs(wp - (long long)s * back, v);
+        }
+    }
+    o.dec += (size_t)dots * (size_t)p.C;
+    o.wk += 1;
+}
 
 // Unscaled envelope sample.  ENV 1: |y|.  ENV 2: the one-pole state w[t] = k*w[t-1] + |y[t]|; the
 // butter(1) low-pass output is b0*(w[t] + w[t-1]) (same transfer function (1+z^-1)/(1-k*z^-1) as
@@ -279,8 +303,12 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
                     if (ENV == 2) vp = (r == j) ? ev[j - 1] : vp;
                 }
                 if (ENV == 2) v += vp;
-                if (active) __stcs(o.dec, o.env_scale * v);
-                o.dec += o.C;
+                if (OUT == 3) {
+                    store_window_entries(p, o, o.env_scale * v, active);
+                } else {
+                    if (active) __stcs(o.dec, o.env_scale * v);
+                    o.dec += o.C;
+                }
                 o.next_dec += o.step;
             }
         }
@@ -304,8 +332,12 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             }
         }
         if (OUT > 0 && ENV > 0 && o.dec && o.next_dec == t + i) {
-            if (active) __stcs(o.dec, o.env_scale * out);
-            o.dec += o.C;
+            if (OUT == 3) {
+                store_window_entries(p, o, o.env_scale * out, active);
+            } else {
+                if (active) __stcs(o.dec, o.env_scale * out);
+                o.dec += o.C;
+            }
             o.next_dec += o.step;
         }
     }
@@ -355,7 +387,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
     const int t0 = item.t0, t1 = item.t1;
     int tE0 = n - p.w_edge;
     tE0 = tE0 > 0 ? (tE0 / kTile) * kTile : 0;
-    const bool need_env = p.env_t != nullptr || p.dec != nullptr;
+    const bool need_env = p.env_t != nullptr || p.dec != nullptr || p.win != nullptr;
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
     const bool full_out = p.gfb_t != nullptr || p.env_t != nullptr;
     const int nE = (need_imag && !EDGE) ? (n - tE0 + kTile - 1) / kTile : 0;
@@ -409,7 +441,15 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
         if (t0 > p.phase) j0 = (t0 - p.phase + p.step - 1) / p.step;
         o.next_dec = p.phase + j0 * p.step;
         o.dec = p.dec ? p.dec + (size_t)(ut.dec_off + j0) * o.C + (active ? c : 0) : nullptr;
+        o.wk = j0;
+        o.nwin = 0;
+        if (p.win && !full_out) {  // window mode: o.dec walks the slot-0 entries instead
+            const long long row0 = p.win_off[item.utt];
+            o.nwin = (int)(p.win_off[item.utt + 1] - row0);
+            o.dec = p.win + (size_t)(row0 + j0) * (size_t)p.win_dots * o.C + (active ? c : 0);
+        }
     }
+    const bool win_mode = p.win != nullptr && !full_out;
 
     for (int kk = 0; kk < total; ++kk) {
         const int b = kk % kStages;
@@ -464,6 +504,9 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
                 if (p.lpf) run_tile<FORM, 2, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else if (need_env) run_tile<FORM, 1, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else run_tile<FORM, 0, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+            } else if (win_mode) {
+                if (p.lpf) run_tile<FORM, 2, 3, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<FORM, 1, 3, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else {
                 if (p.lpf) run_tile<FORM, 2, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else run_tile<FORM, 1, 1, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);

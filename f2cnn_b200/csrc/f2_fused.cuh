@@ -13,6 +13,9 @@ struct FusedParams {
     float* gfb_t;        // full-rate filterbank output, time-major [t][C]   (nullable)
     float* env_t;        // full-rate envelope, time-major [t][C]            (nullable)
     float* dec;          // decimated envelope frames [frame][C]             (nullable)
+    float* win;          // windows of win_dots consecutive frames [row][win_dots][C]   (nullable)
+    const long long* win_off;  // [n_utts+1] first window row of each utterance
+    int win_dots;
     const float* edge;   // precomputed edge residuals [utt][C][8] (f2_edge.cu); null: compute in-kernel
     int C;
     int c_pad;

@@ -114,6 +114,7 @@ class Batch:
         check(L.f2_batch_frame_offsets(self._h, self.frame_offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
         self.sample_offsets = np.zeros(self.n_utts + 1, dtype=np.int64)
         np.cumsum(self.lengths, out=self.sample_offsets[1:])
+        self._grid = {}
 
     def __del__(self):
         try:
@@ -127,12 +128,26 @@ class Batch:
     def workspace_bytes(self, want_full_gfb=False, want_full_env=False):
         return int(_native.lib().f2_batch_workspace_bytes(self._h, int(want_full_gfb), int(want_full_env)))
 
+    def grid_windows(self, dots=11):
+        """The label grid of LabelDataGenerator.py:38-50 on this batch's decimated frames: utterance
+        u has nb = max(n // step - dots - 1, 0) windows, window k = frames k .. k+dots-1.  Returns the
+        device int64 row offsets (n_utts+1) `run(windows=...)` wants, and the total row count."""
+        key = int(dots)
+        if key not in self._grid:
+            nb = np.maximum(self.lengths // self.step - key - 1, 0)
+            off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+            self._grid[key] = (torch.from_numpy(off).to(self.plan.device), int(off[-1]))
+        return self._grid[key]
+
     def run(self, wave_dev, lpf=False, cutoff=100, gfb=None, env=None, env_t=False, dec=False, stream=None,
-            out=None, fused_events=None):
+            out=None, fused_events=None, windows=None):
         """wave_dev: flat device tensor (int16/float32/float64) of total_samples.
         gfb/env: None or torch.float64/float32 -> (C*total_samples,) reference-layout blocks;
         env_t: time-major [total_samples, C] float32; dec: [total_frames, C] float32.
-        `out` may carry preallocated tensors under the same keys."""
+        `out` may carry preallocated tensors under the same keys.
+        windows=(row_offsets_dev, dots[, out_tensor]): the fused kernel writes the (rows, dots, C)
+        float32 windows itself (window k of utterance u = its decimated frames k..k+dots-1, rows
+        row_offsets[u] + k); a stand-alone output mode, see grid_windows()."""
         plan = self.plan
         C = plan.n_channels
         if wave_dev.numel() != self.total_samples:
@@ -160,6 +175,20 @@ class Batch:
         a.env_dtype = _T2F2[e.dtype] if e is not None else F2_F64
         a.env_t = res["env_t"].data_ptr() if "env_t" in res else None
         a.dec = res["dec"].data_ptr() if "dec" in res else None
+        if windows is not None:
+            if g is not None or e is not None or "env_t" in res or "dec" in res:
+                raise ValueError("windows is a stand-alone output mode")
+            offs, dots = windows[0], int(windows[1])
+            if offs.dtype != torch.int64 or offs.device != plan.device or offs.numel() != len(self.lengths) + 1:
+                raise ValueError("windows offsets: int64 device tensor of n_utts+1 entries")
+            if len(windows) > 2 and windows[2] is not None:
+                res["windows"] = windows[2]
+            elif "windows" not in res:
+                res["windows"] = torch.empty((int(offs[-1].item()), dots, C), dtype=torch.float32, device=plan.device)
+            w = res["windows"]
+            if w.dtype != torch.float32 or not w.is_contiguous() or w.device != plan.device:
+                raise ValueError("windows output: contiguous float32 tensor on the plan's device")
+            a.windows, a.win_offsets, a.win_dots = w.data_ptr(), offs.data_ptr(), dots
         if fused_events is not None:  # (DeviceEvent, DeviceEvent) around the fused kernel
             a.ev_fused_start, a.ev_fused_stop = fused_events[0].handle, fused_events[1].handle
         need = self.workspace_bytes(g is not None, e is not None and "env_t" not in res)
@@ -279,8 +308,15 @@ class WindowPipeline:
             batch = plan.batch(lengths[a:b], step=step, phase=phase, target_items=1)
             base = np.concatenate([batch.frame_offsets[u - a] + np.asarray(bases[u], dtype=np.int64)
                                    for u in range(a, b)] + [np.zeros(0, dtype=np.int64)])
+            # windows that are exactly the label grid (window k = frames k..k+dots-1, k < nb) are written by
+            # the fused kernel itself; anything else goes through the decimated frames and the gather
+            nb = np.maximum(lengths[a:b] // int(step) - self.dots - 1, 0)
+            grid = all(len(bases[u]) == nb[u - a] and
+                       (nb[u - a] == 0 or np.array_equal(np.asarray(bases[u]), np.arange(nb[u - a])))
+                       for u in range(a, b))
             self.subs.append(dict(batch=batch, base=torch.from_numpy(base).to(dev), s0=int(cum[a]), s1=int(cum[b]),
-                                  r0=row, r1=row + int(base.shape[0])))
+                                  r0=row, r1=row + int(base.shape[0]),
+                                  grid=batch.grid_windows(self.dots)[0] if grid else None))
             row += int(base.shape[0])
         self.n_windows = row
         C = plan.n_channels
@@ -319,11 +355,16 @@ class WindowPipeline:
             if i >= 2:
                 comp.wait_event(self._ev_free[k])  # the D2H of sub-batch i-2 has drained this buffer
             n_w = sub["r1"] - sub["r0"]
-            sub["batch"].run(self._wave[k][:n_s], lpf=self.lpf, cutoff=self.cutoff,
-                             out={"dec": self._dec[:max(sub["batch"].total_frames, 1)]})
-            self._ev_wave_free[k].record(comp)
-            if n_w:
-                gather_windows(self._dec, sub["base"], self.dots, 1, out=self._win[k][:n_w])
+            if sub["grid"] is not None and n_w:
+                sub["batch"].run(self._wave[k][:n_s], lpf=self.lpf, cutoff=self.cutoff,
+                                 windows=(sub["grid"], self.dots, self._win[k][:n_w]))
+                self._ev_wave_free[k].record(comp)
+            else:
+                sub["batch"].run(self._wave[k][:n_s], lpf=self.lpf, cutoff=self.cutoff,
+                                 out={"dec": self._dec[:max(sub["batch"].total_frames, 1)]})
+                self._ev_wave_free[k].record(comp)
+                if n_w:
+                    gather_windows(self._dec, sub["base"], self.dots, 1, out=self._win[k][:n_w])
             self._ev_done[k].record(comp)
             with torch.cuda.stream(self._s_out):
                 self._s_out.wait_event(self._ev_done[k])

@@ -96,6 +96,15 @@ typedef struct f2_run_args {
     float* dec;       /* out, nullable: decimated envelope frames [total_frames][C] float32 */
     void* ev_fused_start; /* nullable cudaEvent_t recorded on `stream` right before ...     */
     void* ev_fused_stop;  /* ... and right after the fused kernel (for roofline timing)     */
+    /* Windows on the decimated grid written by the fused kernel itself (the rows GenerateInputData
+     * builds for a label CSV whose timepoints are consecutive grid steps, InputGenerator.py:73-83 with
+     * LabelDataGenerator.py:48-50): window k of utterance u = decimated frames k .. k+win_dots-1, for
+     * k < win_offsets[u+1] - win_offsets[u]; it is row win_offsets[u] + k of `windows`
+     * ([rows][win_dots][C] float32).  win_offsets: DEVICE array of n_utts+1 row offsets.  Arbitrary
+     * timepoints take `dec` + f2_gather_windows instead. */
+    float* windows;             /* out, nullable */
+    const int64_t* win_offsets; /* device, required with windows */
+    int win_dots;               /* 2*RADIUS+1 */
 } f2_run_args;
 
 /* Replaces, fused: filters.erb_filterbank (gammatone/filters.py:195-239),

@@ -476,3 +476,42 @@ def test_warmup_lengths_are_what_keeps_truncation_below_float32(gpu, oracle):
     assert plan.get_warmup() == (256, 256, 256)
     bad = plan.batch([30000], target_items=8).run(wd, lpf=True, cutoff=50, env=torch.float64)["env"].cpu().numpy()
     assert rel_err(bad.reshape(128, -1), eo).max() > 10 * TOL
+
+
+def test_fused_window_store_equals_decimated_frames_plus_gather(gpu, oracle):
+    """`windows` output mode of f2_batch_run: for the label grid (window k = decimated frames
+    k..k+dots-1, k < max(n//step - dots - 1, 0): LabelDataGenerator.py:38-50 + InputGenerator.py:73-80)
+    the fused kernel stores every frame into the window rows that contain it.  Pure placement: bit
+    for bit the decimated frames + gather, on ragged batches with too-short utterances, with time
+    chunks, other radii / steps, a channel count that is not a multiple of 32, with and without
+    low-pass; and equal to the oracle's windows."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    for C, lens, dots, step, lpf, target in (
+            (128, [9000, 1700, 48000, 1919, 1920, 2081, 33000], 11, 160, True, 0),
+            (128, [60000], 11, 160, True, 64),            # one utterance in time chunks
+            (40, [5000, 12345, 800], 5, 80, False, 0),
+            (7, [4000, 4001], 3, 100, True, 16)):
+        co = filters.make_erb_filters(16000, filters.centre_freqs(16000, C, 100))
+        waves = [synth.white_noise_i16(n, seed=40 + i) for i, n in enumerate(lens)]
+        flat = torch.from_numpy(np.concatenate(waves)).cuda()
+        plan = engine.plan_for(co)
+        batch = plan.batch(lens, step=step, target_items=target)
+        offs, rows = batch.grid_windows(dots)
+        nb = [max(n // step - dots - 1, 0) for n in lens]
+        assert rows == sum(nb) and offs.cpu().tolist() == np.concatenate([[0], np.cumsum(nb)]).tolist()
+        win = torch.full((rows, dots, C), float("nan"), dtype=torch.float32, device="cuda")
+        batch.run(flat, lpf=lpf, cutoff=50, windows=(offs, dots, win))
+        dec = batch.run(flat, lpf=lpf, cutoff=50, dec=True)["dec"]
+        base = np.concatenate([batch.frame_offsets[u] + np.arange(nb[u]) for u in range(len(lens))]).astype(np.int64)
+        want = engine.gather_windows(dec, torch.from_numpy(base).cuda(), dots, 1)
+        assert not torch.isnan(win).any()          # every entry of every row was written
+        assert torch.equal(win, want)
+        # and against the reference algorithm: rows of GenerateInputData for that label grid
+        u = int(np.argmax(lens))
+        _, eo, wo = oracle.utterance(waves[u], co, lpf, 50, step * (dots // 2) + step * np.arange(nb[u]), dots // 2, step)
+        r0 = int(offs[u].item())
+        scale = np.sqrt(np.mean(eo ** 2, axis=1))
+        assert np.max(np.abs(win[r0:r0 + nb[u]].cpu().numpy() - wo) / scale[None, None, :]) <= TOL
+    with pytest.raises(ValueError):
+        batch.run(flat, lpf=True, cutoff=50, dec=True, windows=(offs, dots, win))
