@@ -317,16 +317,19 @@ def main():
     roofline = {"bound": "fp32_fma", "kernel": "fused_kernel", "achieved": achieved, "peak": fma_peak,
                 "unit": "TFLOP/s", "frac": achieved / fma_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one fused_kernel launch on this workload,
-                # ncu --set full capture summarised in profiles/r01o_ncu_final.md (algorithmic: 3.37e9;
-                # the one-warp CTAs of an utterance drift apart in time and re-read ~65 % of the ring tiles
-                # that have left L2 -- 1.7 % of HBM peak, the kernel is FMA-bound)
-                "traffic": 5.523e9 if args.utts == N_UTTS else None,
+                # ncu --set full capture summarised in profiles/r01p_ncu_final.md: 6.15 GB read + 7.45 GB
+                # written.  Algorithmic: 2.9 GB of ring tiles + 7.5 GB of windows = 10.4 GB; the one-warp CTAs
+                # of an utterance drift apart in time and re-read the ring tiles that have left L2 -- 4 % of
+                # HBM peak, the kernel is FMA-bound
+                "traffic": 13.595e9 if args.utts == N_UTTS else None,
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 entry); "
                                "tools/fma_peak.cu measured 73.8 TFLOP/s sustained (FFMA2) on this pool",
                 "kernel_ms": fused_ms, "kernel_share_of_step": fused_ms / ms_step,
                 "algorithmic_flop_per_channel_sample": FLOP_PER_CS,
-                "hbm": {"algorithmic_bytes_per_channel_sample": 12.0 / C + 4.0 / STEP,
-                        "achieved_GBps": (12.0 / C + 4.0 / STEP) * cs_per_step / (fused_ms * 1e-3) / 1e9,
+                # ring tiles (x, xi, G: 12 B per sample, shared by the C channels) + every decimated frame
+                # stored into the 2R+1 window rows that contain it
+                "hbm": {"algorithmic_bytes_per_channel_sample": 12.0 / C + 4.0 * dots / STEP,
+                        "achieved_GBps": (12.0 / C + 4.0 * dots / STEP) * cs_per_step / (fused_ms * 1e-3) / 1e9,
                         "peak_GBps": peaks.get("hbm_gbs")}}
     cpu = None
     if not args.no_cpu:
