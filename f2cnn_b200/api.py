@@ -142,19 +142,31 @@ def window_indices(n, centers, radius, step):
 def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=5, step=160, device_out=False):
     """Fused path from waveforms to the (N, 2R+1, C) float32 input tensor.
 
-    waves: list of 1-D arrays (same dtype); timepoints: list of int arrays (window centres
-    per utterance, in output order).  Equivalent to erb_filterbank ->
+    waves: list of 1-D arrays (same dtype), or (flat, lengths) as returned by ingest.read_corpus
+    (one buffer of all samples, pinned for full speed); timepoints: list of int arrays (window
+    centres per utterance, in output order).  Equivalent to erb_filterbank ->
     ExtractEnvelopeFromMatrix(LPF, CUTOFF) -> the gather of InputGenerator.py:73-80 per
     utterance, rows concatenated in list order."""
     coefs = np.asarray(coefs, dtype=np.float64)
     plan = engine.plan_for(coefs)
     C = plan.n_channels
     dots = 2 * radius + 1
-    waves = [_as_wave(w) for w in waves]
-    dts = {w.dtype for w in waves}
-    if len(dts) > 1:
-        waves = [w.astype(np.float64) for w in waves]
-    lengths = np.asarray([w.shape[0] for w in waves], dtype=np.int64)
+    flat_in = None
+    if isinstance(waves, tuple) and len(waves) == 2:
+        flat_in, lengths = waves
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        if not torch.is_tensor(flat_in):
+            flat_in = torch.from_numpy(_as_wave(flat_in))
+        if flat_in.dim() != 1 or flat_in.numel() != int(lengths.sum()):
+            raise ValueError("flat buffer holds %d samples, lengths add up to %d" % (flat_in.numel(), int(lengths.sum())))
+        n_utts = int(lengths.shape[0])
+    else:
+        waves = [_as_wave(w) for w in waves]
+        dts = {w.dtype for w in waves}
+        if len(dts) > 1:
+            waves = [w.astype(np.float64) for w in waves]
+        lengths = np.asarray([w.shape[0] for w in waves], dtype=np.int64)
+        n_utts = len(waves)
     idx = [window_indices(int(n), tp, radius, step) for n, tp in zip(lengths, timepoints)]
     total = int(sum(i.shape[0] for i in idx))
     if total == 0:
@@ -163,19 +175,21 @@ def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=
     allidx = np.concatenate([i.reshape(-1) for i in idx if i.size])
     phase = int(allidx[0] % step)
     on_grid = bool(np.all(allidx % step == phase))
-    flat = np.concatenate(waves) if len(waves) > 1 else waves[0]
+    if flat_in is None:
+        flat_in = torch.from_numpy(np.concatenate(waves) if len(waves) > 1 else waves[0])
     strided = on_grid and all(bool(np.all(np.diff(i, axis=1) == step)) for i in idx if i.size)
-    if strided and not device_out and total * dots * C * 4 >= _PIPELINE_BYTES and len(waves) >= 8:
+    if strided and not device_out and total * dots * C * 4 >= _PIPELINE_BYTES and n_utts >= 8:
         # corpus-sized request: overlap H2D / compute / D2H over sub-batches (PCIe-bound path)
         bases = [(i[:, 0] - phase) // step if i.size else np.zeros(0, dtype=np.int64) for i in idx]
         pipe = engine.WindowPipeline(plan, lengths, bases, dots=dots, step=step, phase=phase, lpf=LPF, cutoff=CUTOFF,
-                                     n_sub=max(2, min(24, len(waves) // 64)))
-        wave_host = torch.from_numpy(flat).pin_memory()
+                                     n_sub=max(2, min(24, n_utts // 64)))
+        wave_host = flat_in if flat_in.is_pinned() else flat_in.pin_memory()
         out_host = torch.empty((total, dots, C), dtype=torch.float32, pin_memory=True)
         pipe.run(wave_host, out_host)
         torch.cuda.current_stream().synchronize()
         return out_host.numpy()
-    wave_dev = _to_device(flat, plan.device)
+    wave_dev = (flat_in if flat_in.is_pinned() or flat_in.numel() * flat_in.element_size() < (1 << 16)
+                else flat_in.pin_memory()).to(plan.device, non_blocking=True)
     if on_grid:
         batch = plan.batch(lengths, step=step, phase=phase)
         res = batch.run(wave_dev, lpf=LPF, cutoff=CUTOFF, dec=True)

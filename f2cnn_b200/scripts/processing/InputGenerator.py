@@ -53,13 +53,17 @@ def _say_lpf(LPF, CUTOFF):
 def _fill_from_waveforms(pending, out, cfg, rate, channels, radius, step, LPF, CUTOFF):
     """pending: [(first row, wav path, timepoints)].  One batch for all of them."""
     from concurrent.futures import ThreadPoolExecutor
-    from ... import api
+    from ... import api, ingest
     from ...gammatone import filters
     from .GammatoneFiltering import GetArrayFromWAV
     low = cfg.getint('FILTERBANK', 'LOW_FREQ')
     coefs = filters.make_erb_filters(rate, filters.centre_freqs(rate, channels, low))
-    with ThreadPoolExecutor(max_workers=8) as readers:
-        waves = [samples for _, samples in readers.map(GetArrayFromWAV, [p[1] for p in pending])]
+    try:  # mono 16-bit PCM (TIMIT): straight into one pinned buffer
+        flat, lengths, _ = ingest.read_corpus([p[1] for p in pending])
+        waves = (flat, lengths)
+    except ValueError:  # anything else (e.g. the float64 WAVs of `cnn evalnoise`): decode file by file
+        with ThreadPoolExecutor(max_workers=8) as readers:
+            waves = [samples for _, samples in readers.map(GetArrayFromWAV, [p[1] for p in pending])]
     rows = api.features_to_windows(waves, coefs, [p[2] for p in pending], LPF, CUTOFF, radius, step)
     cursor = 0
     for first, _, points in pending:

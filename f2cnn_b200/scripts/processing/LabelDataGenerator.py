@@ -17,7 +17,6 @@ from the WAV header instead of decoding the file.
 import csv
 import glob
 import os
-import struct
 import time
 from configparser import ConfigParser
 
@@ -29,34 +28,9 @@ from .PHNFileReader import SILENTS, ExtractPhonemes, phoneme_at
 
 def wav_shape(wavFile):
     """(framerate, number of samples) from the header of a RIFF or NIST SPHERE file."""
-    with open(wavFile, 'rb') as handle:
-        head = handle.read(12)
-        if head[:4] == b'RIFF':
-            rate = block = None
-            while True:
-                chunk = handle.read(8)
-                if len(chunk) < 8:
-                    raise ValueError("no data chunk in {}".format(wavFile))
-                tag, size = chunk[:4], struct.unpack('<I', chunk[4:])[0]
-                if tag == b'fmt ':
-                    fmt = handle.read(size + (size & 1))
-                    rate = struct.unpack('<I', fmt[4:8])[0]
-                    block = struct.unpack('<H', fmt[12:14])[0]
-                elif tag == b'data':
-                    return rate, size // block
-                else:
-                    handle.seek(size + (size & 1), 1)
-        if not head.startswith(b'NIST_1A'):
-            raise ValueError("{} is neither RIFF nor NIST SPHERE".format(wavFile))
-        handle.seek(0)
-        handle.readline()
-        text = handle.read(int(handle.readline().strip()) - 16).decode('ascii', 'replace')
-    fields = {}
-    for line in text.splitlines():
-        tokens = line.split(None, 2)
-        if len(tokens) == 3:
-            fields[tokens[0]] = tokens[2]
-    return int(fields['sample_rate']), int(fields['sample_count'])
+    from ...ingest import wav_layout
+    layout = wav_layout(wavFile)
+    return layout.rate, layout.samples
 
 
 class _Geometry:

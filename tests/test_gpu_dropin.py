@@ -183,3 +183,31 @@ def test_evaluating_front_end_and_driver(tree, oracle, monkeypatch):
         assert n > 0 and acc == good / n
     finally:
         dropin.uninstall()
+
+
+def test_features_to_windows_from_one_ingested_buffer(tree, oracle):
+    """ingest.read_corpus -> api.features_to_windows((flat, lengths), ...) equals the list-of-arrays
+    call bit for bit and the oracle within the bar."""
+    import torch
+    assert torch.cuda.is_available()
+    tmp_path, waves = tree
+    from f2cnn_b200 import api, ingest, synth
+    from f2cnn_b200.gammatone import filters
+    co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 32, 100))
+    keys = sorted(waves)
+    paths = [str(tmp_path / "resources" / "f2cnn" / tt / (name + ".WAV")) for tt, name in keys]
+    flat, lengths, rates = ingest.read_corpus(paths)
+    assert rates == [16000] * 3 and lengths.tolist() == [len(waves[k]) for k in keys]
+    assert flat.is_pinned() and np.array_equal(flat.numpy(), np.concatenate([waves[k] for k in keys]))
+    tps = [synth.label_grid(int(n))[::3] for n in lengths]
+    a = api.features_to_windows((flat, lengths), co, tps, True, 50)
+    b = api.features_to_windows([waves[k] for k in keys], co, tps, True, 50)
+    assert a.dtype == np.float32 and np.array_equal(a, b)
+    row = 0
+    for k, tp in zip(keys, tps):
+        _, eo, wo = oracle.utterance(waves[k], co, True, 50, tp)
+        scale = np.sqrt(np.mean(eo ** 2, axis=1))
+        assert np.max(np.abs(a[row:row + len(tp)] - wo) / scale[None, None, :]) <= TOL
+        row += len(tp)
+    with pytest.raises(ValueError):
+        api.features_to_windows((flat[:-1], lengths), co, tps, True, 50)

@@ -237,3 +237,52 @@ def test_input_generator_label_table_and_sphere_reader(tmp_path):
     bad.write_bytes(b"JUNKJUNKJUNK")
     with pytest.raises(ValueError):
         GetArrayFromWAV(str(bad))
+
+
+def test_batched_wav_ingest(tmp_path):
+    """ingest.read_corpus: RIFF and NIST SPHERE (both byte orders) files land back to back in one int16
+    buffer, equal to what GetArrayFromWAV decodes file by file (GammatoneFiltering.py:28-39)."""
+    from scipy.io import wavfile
+    from f2cnn_b200 import ingest, synth
+    from f2cnn_b200.scripts.processing.GammatoneFiltering import GetArrayFromWAV
+    paths, want = [], []
+    for i, n in enumerate((4000, 1, 12345)):
+        w = synth.white_noise_i16(n, seed=70 + i)
+        p = str(tmp_path / ("r%d.WAV" % i))
+        wavfile.write(p, 16000, w)
+        paths.append(p)
+        want.append(w)
+    for fmt, dt in (("01", "<i2"), ("10", ">i2")):
+        w = synth.speech_like_i16(5000, seed=int(fmt))
+        head = ("NIST_1A\n   1024\nsample_count -i {}\nsample_rate -i 8000\nchannel_count -i 1\nsample_n_bytes -i 2\n"
+                "sample_byte_format -s2 {}\nsample_coding -s3 pcm\nend_head\n").format(len(w), fmt).encode()
+        p = str(tmp_path / ("s%s.WAV" % fmt))
+        with open(p, "wb") as f:
+            f.write(head.ljust(1024, b" ") + w.astype(dt).tobytes())
+        paths.append(p)
+        want.append(w)
+    flat, lengths, rates = ingest.read_corpus(paths, threads=3)
+    assert flat.dtype.is_floating_point is False and flat.numel() == sum(len(w) for w in want)
+    assert lengths.tolist() == [len(w) for w in want] and rates == [16000, 16000, 16000, 8000, 8000]
+    assert np.array_equal(flat.numpy(), np.concatenate(want))
+    for p, w in zip(paths, want):
+        rate, got = GetArrayFromWAV(p)
+        assert np.array_equal(got, w)
+        lay = ingest.wav_layout(p)
+        assert lay.samples == len(w) and lay.is_int16_mono and lay.rate == rate
+    # formats the batched reader refuses (the callers fall back to GetArrayFromWAV)
+    f64 = str(tmp_path / "f64.WAV")
+    wavfile.write(f64, 16000, np.zeros(100, dtype=np.float64))
+    assert not ingest.wav_layout(f64).is_int16_mono
+    with pytest.raises(ValueError):
+        ingest.read_corpus([paths[0], f64])
+    stereo = str(tmp_path / "st.WAV")
+    wavfile.write(stereo, 16000, np.zeros((50, 2), dtype=np.int16))
+    assert ingest.wav_layout(stereo).channels == 2
+    with pytest.raises(ValueError):
+        ingest.read_corpus([stereo])
+    with open(paths[0], "r+b") as f:  # truncated payload
+        f.truncate(os.path.getsize(paths[0]) - 10)
+    with pytest.raises(ValueError):
+        ingest.read_corpus([paths[0]])
+    assert ingest.read_corpus([])[0].numel() == 0
