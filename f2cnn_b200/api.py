@@ -40,16 +40,16 @@ def _to_host(t):
     return host.numpy()
 
 
-def erb_filterbank(wave, coefs):
-    """gammatone/filters.py:195-239 -> (C, n) float64."""
+def erb_filterbank(wave, coefs, dtype=np.float64):
+    """gammatone/filters.py:195-239 -> (C, n) float64 (the reference's dtype; float32 on request)."""
     w = _as_wave(wave)
     coefs = np.asarray(coefs, dtype=np.float64)
     plan = engine.plan_for(coefs)
     n = int(w.shape[0])
     if n == 0:
-        return np.zeros((plan.n_channels, 0))
+        return np.zeros((plan.n_channels, 0), dtype=dtype)
     batch = plan.batch([n])
-    res = batch.run(_to_device(w, plan.device), gfb=torch.float64)
+    res = batch.run(_to_device(w, plan.device), gfb=torch.float64 if np.dtype(dtype) == np.float64 else torch.float32)
     return _to_host(res["gfb"]).reshape(plan.n_channels, n)
 
 
@@ -72,9 +72,10 @@ def filterbank_envelope(wave, coefs, LPF=False, CUTOFF=100, with_gfb=False, dtyp
     return env
 
 
-def extract_envelope_from_matrix(matrix, LPF=False, CUTOFF=100):
+def extract_envelope_from_matrix(matrix, LPF=False, CUTOFF=100, dtype=np.float64):
     """scripts/processing/EnvelopeExtraction.py:51-67 on an arbitrary (rows, n) matrix:
-    abs(paddedHilbert(row)) then lowPassFilter(row, CUTOFF) iff LPF -> float64, same shape."""
+    abs(paddedHilbert(row)) then lowPassFilter(row, CUTOFF) iff LPF -> float64 (float32 on request),
+    same shape."""
     m = np.asarray(matrix)
     if m.ndim != 2:
         raise ValueError("matrix must be two-dimensional (channels x samples)")
@@ -83,12 +84,13 @@ def extract_envelope_from_matrix(matrix, LPF=False, CUTOFF=100):
     m = np.ascontiguousarray(m)
     rows, n = m.shape
     if rows == 0:
-        return np.zeros(m.shape)
+        return np.zeros(m.shape, dtype=dtype)
     if n == 0:
         # paddedHilbert(empty) -> scipy.signal.hilbert raises "N must be positive."
         raise ValueError("N must be positive.")
     plan = engine.any_plan()
-    out = plan.envelope_rows(_to_device(m, plan.device), LPF, CUTOFF, out_dtype=torch.float64)
+    out = plan.envelope_rows(_to_device(m, plan.device), LPF, CUTOFF,
+                             out_dtype=torch.float64 if np.dtype(dtype) == np.float64 else torch.float32)
     return _to_host(out)
 
 

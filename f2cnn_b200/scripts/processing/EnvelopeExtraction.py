@@ -21,6 +21,8 @@ from os.path import join, split, splitext
 
 import numpy
 
+from .GammatoneFiltering import npy_dtype
+
 counter = None
 
 
@@ -97,7 +99,12 @@ def ExtractAllEnvelopes(LPF=False, CUTOFF=100):
             matrix = loading.pop(i).result()
             if i + lookahead < len(found):
                 loading[i + lookahead] = loaders.submit(numpy.load, found[i + lookahead])
-            saving.append(writers.submit(SaveEnvelope, ExtractEnvelopeFromMatrix(matrix, LPF, CUTOFF), name, len(found)))
+            if npy_dtype() is numpy.float64:
+                envelope = ExtractEnvelopeFromMatrix(matrix, LPF, CUTOFF)
+            else:  # opt-in float32 files (F2CNN_B200_NPY_FLOAT32, see GammatoneFiltering)
+                from ... import api
+                envelope = api.extract_envelope_from_matrix(matrix, LPF, CUTOFF, dtype=numpy.float32)
+            saving.append(writers.submit(SaveEnvelope, envelope, name, len(found)))
             while len(saving) > 8:
                 saving.pop(0).result()
         for job in saving:

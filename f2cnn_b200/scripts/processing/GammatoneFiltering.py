@@ -11,7 +11,10 @@ by configF2CNN.conf.
 The filterbank runs on the B200 (libf2cnn_b200.so).  The reference fans the files out over a
 multiprocessing.Pool (:121-125); a CUDA context must not be forked, so the driver keeps one
 thread feeding the GPU and hands finished matrices to writer threads (numpy.save releases the
-GIL while it writes 49 MB per utterance).
+GIL while it writes 49 MB per utterance).  Opt-in: F2CNN_B200_NPY_FLOAT32=1 in the environment
+makes the two file drivers (this one and ExtractAllEnvelopes) store float32 matrices -- half the
+PCIe and disk traffic; every reader of this package takes either dtype.  The array functions keep
+the reference's float64.
 """
 import glob
 import os
@@ -88,6 +91,11 @@ def loadGFBMatrix(filename):
     return numpy.load(filename + '.npy')
 
 
+def npy_dtype():
+    """float64 like the reference, or float32 when F2CNN_B200_NPY_FLOAT32 is set to a non-zero value."""
+    return numpy.float32 if os.environ.get('F2CNN_B200_NPY_FLOAT32', '0') not in ('', '0') else numpy.float64
+
+
 def _gfb_name(wavFile):
     return os.path.splitext(wavFile)[0] + '.GFB'
 
@@ -138,7 +146,11 @@ def FilterAllOrganisedFiles():
     with ThreadPoolExecutor(max_workers=4) as writers:
         for wav in found:
             print("Filtering:\t{}".format(wav))
-            matrix, _ = GetFilteredOutputFromFile(wav, FILTERBANK_COEFFICIENTS)
+            if npy_dtype() is numpy.float64:
+                matrix, _ = GetFilteredOutputFromFile(wav, FILTERBANK_COEFFICIENTS)
+            else:
+                from ... import api
+                matrix = api.erb_filterbank(GetArrayFromWAV(wav)[1], FILTERBANK_COEFFICIENTS, dtype=numpy.float32)
             in_flight.append(writers.submit(_store, wav, matrix, len(found)))
             while len(in_flight) > 8:  # bound the host memory held by queued 49 MB matrices
                 in_flight.pop(0).result()

@@ -211,3 +211,39 @@ def test_features_to_windows_from_one_ingested_buffer(tree, oracle):
         row += len(tp)
     with pytest.raises(ValueError):
         api.features_to_windows((flat[:-1], lengths), co, tps, True, 50)
+
+
+def test_float32_npy_option_of_the_file_drivers(tree, oracle, monkeypatch):
+    """F2CNN_B200_NPY_FLOAT32=1: `prepare filter` / `prepare envelope` store float32 matrices (SURVEY.md
+    8f rank 4); `prepare input` reads them and produces the same rows within float32 rounding."""
+    import torch
+    assert torch.cuda.is_available()
+    tmp_path, waves = tree
+    from f2cnn_b200 import dropin, synth
+    monkeypatch.setenv("F2CNN_B200_NPY_FLOAT32", "1")
+    dropin.install()
+    try:
+        from gammatone import filters
+        from scripts.processing import EnvelopeExtraction, GammatoneFiltering, InputGenerator
+        co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 32, 100))
+        GammatoneFiltering.FilterAllOrganisedFiles()
+        EnvelopeExtraction.ExtractAllEnvelopes(True, 50)
+        rows, want = [], []
+        for (tt, name), w in sorted(waves.items()):
+            base = tmp_path / "resources" / "f2cnn" / tt / name
+            gfb, env = np.load(str(base) + ".GFB.npy"), np.load(str(base) + ".ENV1.npy")
+            assert gfb.dtype == env.dtype == np.float32 and gfb.shape == env.shape == (32, len(w))
+            go, eo, _ = oracle.utterance(w, co, True, 50)
+            assert rel(gfb, go) <= TOL and rel(env, eo) <= 2 * TOL   # envelope of the float32-rounded GFB
+            dr, spk, sent = name.split(".")
+            tps = synth.label_grid(len(w))[::2]
+            rows += [[tt, dr, spk, sent, "aa", int(tp), 0.1, 0.01, 1] for tp in tps]
+            want.append(oracle.gather_windows(env.astype(np.float64), tps))
+        os.makedirs("trainingData")
+        with open(os.path.join("trainingData", "label_data.csv"), "w") as f:
+            csv.writer(f, lineterminator="\n").writerows(rows)
+        InputGenerator.GenerateInputData(LPF=True, CUTOFF=50)
+        out = np.load(os.path.join("trainingData", "input_data_LPF50.npy"))
+        assert out.dtype == np.float32 and np.array_equal(out, np.concatenate(want))
+    finally:
+        dropin.uninstall()
