@@ -59,11 +59,16 @@ def seeded_model(seed=0, dots=11, channels=128, device="cuda", dtype=torch.float
 
 
 @torch.no_grad()
-def predict(model, frames_dev, batch=8192, autocast_dtype=None):
+def predict(model, frames_dev, batch=8192, autocast_dtype=None, channels_last=False):
     """Scores for all frames, in batches (46 240 frames per 3 s utterance).  autocast_dtype =
     torch.bfloat16 runs the convolutions and dense layers on the tensor cores in bf16 (inputs are
-    normalised to [0, 1], scores differ by ~1e-2); None keeps the parameters' precision."""
+    normalised to [0, 1], scores differ by ~1e-2); None keeps the parameters' precision.
+    channels_last=True lays the convolution weights and activations out NHWC, the layout cuDNN's
+    tensor-core kernels want (57 ms fp32 -> 49 ms bf16 -> 33 ms bf16 NHWC per 3 s utterance); it
+    converts the module's parameters in place, the results do not depend on it."""
     out = []
+    if channels_last:
+        model.to(memory_format=torch.channels_last)
     dt = next(model.parameters()).dtype
     for i in range(0, frames_dev.shape[0], batch):
         x = frames_dev[i:i + batch].to(dt)

@@ -298,6 +298,12 @@ def test_evalnoise_config5_frames_and_cnn_forward(gpu, oracle):
         s_ref = cnn.predict(model, torch.from_numpy(want).cuda().float()).cpu().numpy()
         assert s_gpu.shape == (4, 2) and np.allclose(s_gpu.sum(axis=1), 1.0, atol=1e-5)
         assert np.max(np.abs(s_gpu - s_ref)) <= 5e-3
+    # the tensor-core options of the forward pass (bf16 autocast, NHWC layout) against fp32 NCHW
+    many = torch.from_numpy(frames[:512]).cuda().float()
+    s32 = cnn.predict(cnn.seeded_model(0), many).cpu().numpy()
+    s16 = cnn.predict(cnn.seeded_model(0), many, autocast_dtype=torch.bfloat16, channels_last=True).cpu().numpy()
+    s32n = cnn.predict(cnn.seeded_model(0), many, channels_last=True).cpu().numpy()
+    assert np.max(np.abs(s32n - s32)) <= 1e-4 and np.max(np.abs(s16 - s32)) <= 3e-2
 
 
 def test_chunked_batch_uses_per_utterance_edge_table(gpu, oracle):

@@ -52,15 +52,16 @@ for cut in (20, 50, 100):
 base = synth.speech_like_i16(48000, seed=31)
 wave = base + np.random.default_rng(3).normal(scale=300.0, size=48000)
 model = cnn.seeded_model(0)
-def eval_path(cnn_dtype=None, with_cnn=True):
+def eval_path(cnn_dtype=None, with_cnn=True, channels_last=False):
     b5 = plan.batch([48000])
     res = b5.run(torch.from_numpy(wave).cuda(), lpf=True, cutoff=50, env_t=True)
     frames, flag = engine.dense_frames(res["env_t"], 11, 160, 0, 48000 - 1760, normalize=True, out_dtype=torch.float32)
-    return cnn.predict(model, frames, autocast_dtype=cnn_dtype) if with_cnn else frames
+    return cnn.predict(model, frames, autocast_dtype=cnn_dtype, channels_last=channels_last) if with_cnn else frames
 out["config5_eval_frontend_only"] = {"frames": 48000 - 1760, "device_ms": timed(lambda: eval_path(with_cnn=False), reps=5)}
 out["config5_eval_frontend_plus_cnn_fp32"] = {"device_ms": timed(eval_path, reps=5),
                                               "note": "reference: 25 s Python framing + 0.9 s normalise per utterance before Keras"}
 out["config5_eval_frontend_plus_cnn_bf16"] = {"device_ms": timed(lambda: eval_path(torch.bfloat16), reps=5)}
+out["config5_eval_frontend_plus_cnn_bf16_nhwc"] = {"device_ms": timed(lambda: eval_path(torch.bfloat16, channels_last=True), reps=5)}
 # ---- full-rate output modes (HBM-bound per SURVEY.md 8d): 256 corpus utterances ----
 lengths = synth.corpus_lengths(256, seed=1)
 flat, _ = synth.corpus_waves_i16(lengths, seed=1)
