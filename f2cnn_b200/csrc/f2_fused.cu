@@ -548,22 +548,26 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
 
 cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream) {
     if (n_items <= 0) return cudaSuccess;
-    // tuning knob (development only): F2_FUSED_VARIANT = "<min CTAs per SM><unroll>"
+#ifdef F2_FUSED_TUNING
+    // development build (make EXTRA=-DF2_FUSED_TUNING): F2_FUSED_VARIANT = "<min CTAs per SM><unroll>"
     static int variant = -1;
     if (variant < 0) {
         const char* v = getenv("F2_FUSED_VARIANT");
         variant = v ? atoi(v) : 0;
     }
-    if (p.edge) {
-        if (variant == 168) fused_kernel<16, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
-        else fused_kernel<16, 16, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+    if (variant == 168) {
+        if (p.edge) fused_kernel<16, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        else fused_kernel<16, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
         return cudaGetLastError();
     }
-    switch (variant) {
-        case 168: fused_kernel<16, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        case 208: fused_kernel<20, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
-        default: fused_kernel<16, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p); break;
+    if (variant == 208 && !p.edge) {
+        fused_kernel<20, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        return cudaGetLastError();
     }
+#endif
+    // 16 one-warp CTAs per SM, 16 samples per loop trip (profiles/r01j_tune_*.log, r01m)
+    if (p.edge) fused_kernel<16, 16, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+    else fused_kernel<16, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
