@@ -56,6 +56,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int round_up_tile(double v) { return (int)(ceil(v / f2::kTile) * f2::kTile); }
 constexpr float kDirectMinCyGfb = 0.25f;
 constexpr float kDirectMinCyEnv = 0.035f;
+constexpr double kDirectCost = 0.85;  // time per sample of a direct-form group / delta-form group (measured)
 
 // Per-stage float32 rounding whose SUM over the four stages is as close to 4*c as the
 // float32 lattice allows.  The four sections share their poles, so the first-order error of
@@ -314,15 +315,41 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         }
         seg = (long long)align_up((size_t)best, f2::kTile);
     }
+    // Chunks of equal COST, not equal length (automatic policy only): a direct-form group runs a
+    // sample in kDirectCost of a delta-form group's time, so its chunks are longer --
+    // (seg_direct + W) * kDirectCost = seg_delta + W, W = the warm-up every chunk pays -- with the
+    // total number of chunks unchanged.  With about one wave of CTAs (a single long stream) all CTAs
+    // then finish together instead of the delta-form ones finishing last.
+    std::vector<long long> seg_of((size_t)cblocks, seg);
+    if (target_items <= 0 && seg < ((long long)1 << 40)) {
+        int n_direct = 0;
+        std::vector<char> direct((size_t)cblocks, 0);
+        for (int cb = 0; cb < cblocks; ++cb) {
+            direct[(size_t)cb] = plan->h_chan[(size_t)f2::P_FORM * plan->c_pad + (size_t)cb * 32] >= kDirectMinCyEnv;
+            n_direct += direct[(size_t)cb];
+        }
+        if (n_direct > 0 && n_direct < cblocks) {
+            const double fd = (double)n_direct / cblocks, W = (double)plan->w_casc + 2048.0, s0 = (double)seg;
+            double lo = 2048.0, hi = s0;  // seg_delta
+            for (int it = 0; it < 60; ++it) {
+                const double sD = 0.5 * (lo + hi), sd = (sD + W) / kDirectCost - W;
+                if (fd / sd + (1.0 - fd) / sD > 1.0 / s0) lo = sD; else hi = sD;
+            }
+            const long long sD = (long long)align_up((size_t)std::max(2048.0, 0.5 * (lo + hi)), f2::kTile);
+            const long long sd = (long long)align_up((size_t)std::max(2048.0, ((double)sD + W) / kDirectCost - W), f2::kTile);
+            for (int cb = 0; cb < cblocks; ++cb) seg_of[(size_t)cb] = direct[(size_t)cb] ? sd : sD;
+        }
+    }
     if (target_items <= 0) target_items = 4 * wave_ctas;  // lane-stream decomposition below
     std::vector<f2::Item> items;
     for (int u = 0; u < n_utts; ++u) {
         const int n = b->utts[(size_t)u].n;
         if (n <= 0) continue;
-        const long long nseg = std::max<long long>(1, (n + seg - 1) / seg);
-        const long long len = (long long)align_up((size_t)((n + nseg - 1) / nseg), f2::kTile);
-        for (long long t0 = 0; t0 < n; t0 += len)
-            for (int cb = 0; cb < cblocks; ++cb) {
+        for (int cb = 0; cb < cblocks; ++cb) {
+            const long long sg = seg_of[(size_t)cb];
+            const long long nseg = std::max<long long>(1, (n + sg - 1) / sg);
+            const long long len = (long long)align_up((size_t)((n + nseg - 1) / nseg), f2::kTile);
+            for (long long t0 = 0; t0 < n; t0 += len) {
                 f2::Item it;
                 it.utt = u;
                 it.cblock = cb;
@@ -330,8 +357,10 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
                 it.t1 = (int)std::min<long long>(n, t0 + len);
                 items.push_back(it);
             }
+        }
     }
-    // longest first: the hardware dispatches CTAs in index order, so the tail is short items
+    // longest first: the hardware dispatches CTAs in index order, so the tail is short items (the sort
+    // is stable: the channel groups of an unsplit utterance stay adjacent and share ring tiles in L2)
     std::stable_sort(items.begin(), items.end(), [](const f2::Item& a, const f2::Item& c) {
         return (a.t1 - a.t0) > (c.t1 - c.t0);
     });
