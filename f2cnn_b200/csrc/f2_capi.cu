@@ -112,6 +112,10 @@ struct f2_batch {
     long long n_whole = 0;  // items if no utterance were split in time
     f2::UttDesc* d_utts = nullptr;
     f2::Item* d_items = nullptr;
+    // equal-LENGTH chunks for the runs that store the full-rate filterbank output (store-bound: every
+    // channel group costs the same per sample); null when the two decompositions coincide
+    f2::Item* d_items_uniform = nullptr;
+    long long n_items_uniform = 0;
     long long total_samples = 0, total_frames = 0, total_ring = 0;
     int max_n = 0;
     int min_log2 = 0, max_log2 = 0;
@@ -341,30 +345,50 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         }
     }
     if (target_items <= 0) target_items = 4 * wave_ctas;  // lane-stream decomposition below
-    std::vector<f2::Item> items;
-    for (int u = 0; u < n_utts; ++u) {
-        const int n = b->utts[(size_t)u].n;
-        if (n <= 0) continue;
-        for (int cb = 0; cb < cblocks; ++cb) {
-            const long long sg = seg_of[(size_t)cb];
-            const long long nseg = std::max<long long>(1, (n + sg - 1) / sg);
-            const long long len = (long long)align_up((size_t)((n + nseg - 1) / nseg), f2::kTile);
-            for (long long t0 = 0; t0 < n; t0 += len) {
-                f2::Item it;
-                it.utt = u;
-                it.cblock = cb;
-                it.t0 = (int)t0;
-                it.t1 = (int)std::min<long long>(n, t0 + len);
-                items.push_back(it);
+    auto build_items = [&](const std::vector<long long>& segs, bool same_for_all) {
+        std::vector<f2::Item> out;
+        auto push = [&](int u, int cb, long long t0, long long len, int n) {
+            f2::Item it;
+            it.utt = u;
+            it.cblock = cb;
+            it.t0 = (int)t0;
+            it.t1 = (int)std::min<long long>(n, t0 + len);
+            out.push_back(it);
+        };
+        for (int u = 0; u < n_utts; ++u) {
+            const int n = b->utts[(size_t)u].n;
+            if (n <= 0) continue;
+            auto chunk_len = [&](long long sg) {
+                const long long nseg = std::max<long long>(1, (n + sg - 1) / sg);
+                return (long long)align_up((size_t)((n + nseg - 1) / nseg), f2::kTile);
+            };
+            if (same_for_all) {
+                // the channel groups of one time chunk next to each other: they share ring tiles and, in
+                // the full-rate modes, write the same time-major rows
+                const long long len = chunk_len(segs[0]);
+                for (long long t0 = 0; t0 < n; t0 += len)
+                    for (int cb = 0; cb < cblocks; ++cb) push(u, cb, t0, len, n);
+            } else {
+                for (int cb = 0; cb < cblocks; ++cb) {
+                    const long long len = chunk_len(segs[(size_t)cb]);
+                    for (long long t0 = 0; t0 < n; t0 += len) push(u, cb, t0, len, n);
+                }
             }
         }
-    }
-    // longest first: the hardware dispatches CTAs in index order, so the tail is short items (the sort
-    // is stable: the channel groups of an unsplit utterance stay adjacent and share ring tiles in L2)
-    std::stable_sort(items.begin(), items.end(), [](const f2::Item& a, const f2::Item& c) {
-        return (a.t1 - a.t0) > (c.t1 - c.t0);
-    });
+        // longest first: the hardware dispatches CTAs in index order, so the tail is short items (the
+        // sort is stable: neighbours stay neighbours)
+        std::stable_sort(out.begin(), out.end(), [](const f2::Item& a, const f2::Item& c) {
+            return (a.t1 - a.t0) > (c.t1 - c.t0);
+        });
+        return out;
+    };
+    const std::vector<long long> seg_same((size_t)cblocks, seg);
+    const bool equal_cost = seg_of != seg_same;
+    std::vector<f2::Item> items = build_items(seg_of, !equal_cost);
+    std::vector<f2::Item> items_uniform;
+    if (equal_cost) items_uniform = build_items(seg_same, true);
     b->n_items = (long long)items.size();
+    b->n_items_uniform = (long long)items_uniform.size();
     b->n_whole = whole / units * cblocks;  // same utterance count, in CTAs
 
     // ---- lane streams: (utterance, time chunk), 32 per CTA, kLaneWarps channels per CTA ------
@@ -430,6 +454,12 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         e = cudaMalloc(&b->d_items, sizeof(f2::Item) * items.size());
         if (e == cudaSuccess)
             e = cudaMemcpy(b->d_items, items.data(), sizeof(f2::Item) * items.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && !items_uniform.empty()) {
+            e = cudaMalloc(&b->d_items_uniform, sizeof(f2::Item) * items_uniform.size());
+            if (e == cudaSuccess)
+                e = cudaMemcpy(b->d_items_uniform, items_uniform.data(), sizeof(f2::Item) * items_uniform.size(),
+                               cudaMemcpyHostToDevice);
+        }
     }
     if (e == cudaSuccess && b->lanes_ok) {
         e = cudaMalloc(&b->d_streams, sizeof(f2::LaneStream) * b->streams.size());
@@ -441,6 +471,7 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
     if (e != cudaSuccess) {
         if (b->d_utts) cudaFree(b->d_utts);
         if (b->d_items) cudaFree(b->d_items);
+        if (b->d_items_uniform) cudaFree(b->d_items_uniform);
         if (b->d_streams) cudaFree(b->d_streams);
         if (b->d_groups) cudaFree(b->d_groups);
         delete b;
@@ -455,6 +486,7 @@ int f2_batch_destroy(f2_batch* batch) {
     DeviceGuard guard(batch->plan->device);
     if (batch->d_utts) cudaFree(batch->d_utts);
     if (batch->d_items) cudaFree(batch->d_items);
+    if (batch->d_items_uniform) cudaFree(batch->d_items_uniform);
     if (batch->d_streams) cudaFree(batch->d_streams);
     if (batch->d_groups) cudaFree(batch->d_groups);
     delete batch;
@@ -610,7 +642,9 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
 
     f2::FusedParams fp;
     fp.utts = b->d_utts;
-    fp.items = b->d_items;
+    // the filterbank output is store-bound and uses the direct form for fewer groups: equal-length chunks
+    const bool uniform_chunks = gfb_t != nullptr && b->d_items_uniform != nullptr;
+    fp.items = uniform_chunks ? b->d_items_uniform : b->d_items;
     fp.chan = plan->d_chan;
     fp.xz = xz;
     fp.G = G;
@@ -652,7 +686,7 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     // low-pass warm-up of a mid-signal chunk: |a1|^W < 1e-7
     fp.w_lpf = a->lpf ? round_up_tile(log(1e-7) / log(-a1)) : 0;
     if (a->ev_fused_start) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_start, stream));
-    F2_CUDA(f2::launch_fused(fp, (int)b->n_items, stream));
+    F2_CUDA(f2::launch_fused(fp, (int)(uniform_chunks ? b->n_items_uniform : b->n_items), stream));
     if (a->ev_fused_stop) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_stop, stream));
 
     if (a->gfb)
