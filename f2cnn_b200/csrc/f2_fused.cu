@@ -352,7 +352,7 @@ struct Smem {
 // The whole CTA (= one warp = 32 adjacent channels) for one section form.
 // EDGE: the edge residuals come from the per-utterance table (time-chunked batches) instead of
 // the in-kernel pass.
-template <int FORM, int U, bool EDGE>
+template <int FORM, int U, bool EDGE, bool WIN>
 __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& item, const Smem& sm, const int c) {
     const UttDesc ut = p.utts[item.utt];
     const int tid = threadIdx.x;
@@ -387,9 +387,10 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
     const int t0 = item.t0, t1 = item.t1;
     int tE0 = n - p.w_edge;
     tE0 = tE0 > 0 ? (tE0 / kTile) * kTile : 0;
-    const bool need_env = p.env_t != nullptr || p.dec != nullptr || p.win != nullptr;
+    const bool need_env = WIN || p.env_t != nullptr || p.dec != nullptr;
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
-    const bool full_out = p.gfb_t != nullptr || p.env_t != nullptr;
+    // WIN: the window-store instantiation (f2_run_args.windows; no full-rate outputs by contract)
+    const bool full_out = !WIN && (p.gfb_t != nullptr || p.env_t != nullptr);
     const int nE = (need_imag && !EDGE) ? (n - tE0 + kTile - 1) / kTile : 0;
     const int w_lpf = (p.lpf && need_env) ? p.w_lpf : 0;
     int ts, tenv;
@@ -443,13 +444,12 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
         o.dec = p.dec ? p.dec + (size_t)(ut.dec_off + j0) * o.C + (active ? c : 0) : nullptr;
         o.wk = j0;
         o.nwin = 0;
-        if (p.win && !full_out) {  // window mode: o.dec walks the slot-0 entries instead
+        if (WIN) {  // window mode: o.dec walks the slot-0 entries instead
             const long long row0 = p.win_off[item.utt];
             o.nwin = (int)(p.win_off[item.utt + 1] - row0);
             o.dec = p.win + (size_t)(row0 + j0) * (size_t)p.win_dots * o.C + (active ? c : 0);
         }
     }
-    const bool win_mode = p.win != nullptr && !full_out;
 
     for (int kk = 0; kk < total; ++kk) {
         const int b = kk % kStages;
@@ -504,7 +504,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
                 if (p.lpf) run_tile<FORM, 2, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else if (need_env) run_tile<FORM, 1, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else run_tile<FORM, 0, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-            } else if (win_mode) {
+            } else if (WIN) {
                 if (p.lpf) run_tile<FORM, 2, 3, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else run_tile<FORM, 1, 3, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else {
@@ -521,7 +521,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
 // separate straight-line programs behind one branch, and a warp that finishes early (direct
 // form: 3 FMAs per section instead of 4) frees its slot for the next work item instead of
 // waiting at a CTA barrier for slower warps (measured: DESIGN.md section 6).
-template <int MINB, int U, bool EDGE>
+template <int MINB, int U, bool EDGE, bool WIN>
 __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedParams p) {
     static_assert(kChanPerBlock == 32, "one warp per CTA: __syncwarp is the only barrier used");
     __shared__ __align__(128) float2 s_xz[kStages][kTile];
@@ -539,11 +539,22 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     const float group_cy = p.chan[P_FORM * p.c_pad + c];
 #ifdef F2_SINGLE_FORM
     (void)group_cy;
-    fused_body<F2_SINGLE_FORM, U, EDGE>(p, item, sm, c);
+    fused_body<F2_SINGLE_FORM, U, EDGE, WIN>(p, item, sm, c);
 #else
-    if (group_cy >= p.direct_min_cy) fused_body<1, U, EDGE>(p, item, sm, c);
-    else fused_body<0, U, EDGE>(p, item, sm, c);
+    if (group_cy >= p.direct_min_cy) fused_body<1, U, EDGE, WIN>(p, item, sm, c);
+    else fused_body<0, U, EDGE, WIN>(p, item, sm, c);
 #endif
+}
+
+template <int MINB, int U>
+static void launch_variant(const FusedParams& p, int n_items, cudaStream_t stream) {
+    if (p.win) {
+        if (p.edge) fused_kernel<MINB, U, true, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        else fused_kernel<MINB, U, false, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+    } else {
+        if (p.edge) fused_kernel<MINB, U, true, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        else fused_kernel<MINB, U, false, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+    }
 }
 
 cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream) {
@@ -556,18 +567,17 @@ cudaError_t launch_fused(const FusedParams& p, int n_items, cudaStream_t stream)
         variant = v ? atoi(v) : 0;
     }
     if (variant == 168) {
-        if (p.edge) fused_kernel<16, 8, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
-        else fused_kernel<16, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        launch_variant<16, 8>(p, n_items, stream);
         return cudaGetLastError();
     }
-    if (variant == 208 && !p.edge) {
-        fused_kernel<20, 8, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+    if (variant == 208) {
+        launch_variant<20, 8>(p, n_items, stream);
         return cudaGetLastError();
     }
 #endif
-    // 16 one-warp CTAs per SM, 16 samples per loop trip (profiles/r01j_tune_*.log, r01m)
-    if (p.edge) fused_kernel<16, 16, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
-    else fused_kernel<16, 16, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+    // 16 one-warp CTAs per SM, 16 samples per loop trip (profiles/r01j_tune_*.log, r01m); the
+    // window-store mode is its own instantiation so that the other modes keep their code
+    launch_variant<16, 16>(p, n_items, stream);
     return cudaGetLastError();
 }
 
