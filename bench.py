@@ -317,11 +317,11 @@ def main():
     roofline = {"bound": "fp32_fma", "kernel": "fused_kernel", "achieved": achieved, "peak": fma_peak,
                 "unit": "TFLOP/s", "frac": achieved / fma_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one fused_kernel launch on this workload,
-                # ncu --set full capture summarised in profiles/r01p_ncu_final.md: 6.15 GB read + 7.45 GB
+                # ncu --set full capture summarised in profiles/r01s_ncu_final.md: 6.26 GB read + 7.45 GB
                 # written.  Algorithmic: 2.9 GB of ring tiles + 7.5 GB of windows = 10.4 GB; the one-warp CTAs
                 # of an utterance drift apart in time and re-read the ring tiles that have left L2 -- 4 % of
                 # HBM peak, the kernel is FMA-bound
-                "traffic": 13.595e9 if args.utts == N_UTTS else None,
+                "traffic": 13.710e9 if args.utts == N_UTTS else None,
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 entry); "
                                "tools/fma_peak.cu measured 73.8 TFLOP/s sustained (FFMA2) on this pool",
                 "kernel_ms": fused_ms, "kernel_share_of_step": fused_ms / ms_step,

@@ -412,7 +412,7 @@ __device__ __forceinline__ void cols_fast_body(const PrepParams& p, const UttDes
 // The pass that reads the int16 wave is latency-bound at 3 CTAs per SM (74 registers): capped at 64
 // registers it runs 4 CTAs per SM and 15 % faster; the other passes lose from the same cap.
 template <bool INV, bool SRC_WAVE>
-__global__ void __launch_bounds__(kFftThreads, SRC_WAVE ? 4 : 1) fft_cols_fast_kernel(PrepParams p, float* buf) {
+__global__ void __launch_bounds__(kFftThreads, SRC_WAVE ? 4 : 3) fft_cols_fast_kernel(PrepParams p, float* buf) {
     __shared__ float2 sA[kFastPts + kFastPts / 8 + 64];
     const UttDesc ut = p.utts[blockIdx.x];
     const int log2M = ut.log2N2 - 1;
