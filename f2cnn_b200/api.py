@@ -184,7 +184,7 @@ def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=
         # corpus-sized request: overlap H2D / compute / D2H over sub-batches (PCIe-bound path)
         bases = [(i[:, 0] - phase) // step if i.size else np.zeros(0, dtype=np.int64) for i in idx]
         pipe = engine.WindowPipeline(plan, lengths, bases, dots=dots, step=step, phase=phase, lpf=LPF, cutoff=CUTOFF,
-                                     n_sub=max(2, min(24, n_utts // 64)))
+                                     n_sub=max(2, min(16, n_utts // 64)))
         wave_host = flat_in if flat_in.is_pinned() else flat_in.pin_memory()
         out_host = torch.empty((total, dots, C), dtype=torch.float32, pin_memory=True)
         pipe.run(wave_host, out_host)

@@ -297,8 +297,16 @@ class WindowPipeline:
         U = int(lengths.shape[0])
         n_sub = max(1, min(int(n_sub), U))
         cum = np.concatenate([[0], np.cumsum(lengths)])
-        cuts = [int(np.searchsorted(cum, cum[-1] * k / n_sub)) for k in range(n_sub + 1)]
-        cuts[0], cuts[-1] = 0, U
+        # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that: the
+        # D2H copy -- the bottleneck -- cannot start before the first sub-batch is uploaded and computed
+        base = cum[-1] / n_sub
+        marks, size, at = [0.0], base / 8, 0.0
+        while at + size < cum[-1]:
+            at += size
+            marks.append(at)
+            size = min(base, size * 2)
+        cuts = [int(np.searchsorted(cum, m)) for m in marks] + [U]
+        cuts[0] = 0
         cuts = sorted(set(cuts))
         dev = plan.device
         self.subs = []
