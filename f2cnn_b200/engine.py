@@ -299,12 +299,12 @@ class WindowPipeline:
         cum = np.concatenate([[0], np.cumsum(lengths)])
         # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that: the
         # D2H copy -- the bottleneck -- cannot start before the first sub-batch is uploaded and computed
-        base = cum[-1] / n_sub
-        marks, size, at = [0.0], base / 8, 0.0
+        per_sub = cum[-1] / n_sub
+        marks, size, at = [0.0], per_sub / 8, 0.0
         while at + size < cum[-1]:
             at += size
             marks.append(at)
-            size = min(base, size * 2)
+            size = min(per_sub, size * 2)
         cuts = [int(np.searchsorted(cum, m)) for m in marks] + [U]
         cuts[0] = 0
         cuts = sorted(set(cuts))
