@@ -284,8 +284,8 @@ class WindowPipeline:
 
     The utterances are cut into `n_sub` contiguous sub-batches; while sub-batch i is being
     filtered on the compute stream, the windows of sub-batch i-1 travel to the host on a copy
-    stream (double-buffered device output), and the waves of sub-batch i+1 come in on a third
-    stream.  PCIe is the bottleneck of this path (the window tensor is 11x the decimated
+    stream (double-buffered device output); the waves of all sub-batches are uploaded on a third
+    stream right at the start (2 bytes per sample).  PCIe is the bottleneck of this path (the window tensor is 11x the decimated
     envelope), so hiding the 50-odd ms of compute behind the D2H copy is what matters.
 
     bases[u]: int64 array, for every window of utterance u the index (within the utterance)
@@ -328,49 +328,44 @@ class WindowPipeline:
             row += int(base.shape[0])
         self.n_windows = row
         C = plan.n_channels
-        max_s = max(s["s1"] - s["s0"] for s in self.subs)
         max_w = max(s["r1"] - s["r0"] for s in self.subs)
         max_f = max(s["batch"].total_frames for s in self.subs)
-        self._wave = [None, None]
-        self._max_s = max_s
+        self._wave_all = None           # device copy of the whole flat wave buffer (2 B per sample)
+        self._total_s = int(cum[-1])
         self._win = [torch.empty((max(max_w, 1), self.dots, C), dtype=torch.float32, device=dev) for _ in range(2)]
         self._dec = torch.empty((max(max_f, 1), C), dtype=torch.float32, device=dev)
         self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self._ev_in = [torch.cuda.Event() for _ in range(2)]
+        self._ev_in = [torch.cuda.Event() for _ in self.subs]
         self._ev_done = [torch.cuda.Event() for _ in range(2)]
         self._ev_free = [torch.cuda.Event() for _ in range(2)]
-        self._ev_wave_free = [torch.cuda.Event() for _ in range(2)]
 
     def run(self, wave_host, out_host):
         """wave_host: flat (pinned) host tensor of all samples; out_host: (N, dots, C) float32
         host tensor (pinned for full speed).  Returns after everything has landed."""
         comp = torch.cuda.current_stream()
         dev = self.plan.device
-        for k in range(2):
-            if self._wave[k] is None or self._wave[k].dtype != wave_host.dtype:
-                self._wave[k] = torch.empty(self._max_s, dtype=wave_host.dtype, device=dev)
+        if self._wave_all is None or self._wave_all.dtype != wave_host.dtype:
+            self._wave_all = torch.empty(max(self._total_s, 1), dtype=wave_host.dtype, device=dev)
         self._s_in.wait_stream(comp)
         self._s_out.wait_stream(comp)
+        # all uploads are queued at once (444 MB for the corpus): the H2D traffic is over after the first
+        # few milliseconds and the D2H copies -- the bottleneck -- have the link to themselves afterwards
+        with torch.cuda.stream(self._s_in):
+            for i, sub in enumerate(self.subs):
+                self._wave_all[sub["s0"]:sub["s1"]].copy_(wave_host[sub["s0"]:sub["s1"]], non_blocking=True)
+                self._ev_in[i].record(self._s_in)
         for i, sub in enumerate(self.subs):
             k = i & 1
-            n_s = sub["s1"] - sub["s0"]
-            with torch.cuda.stream(self._s_in):
-                if i >= 2:
-                    self._s_in.wait_event(self._ev_wave_free[k])
-                self._wave[k][:n_s].copy_(wave_host[sub["s0"]:sub["s1"]], non_blocking=True)
-                self._ev_in[k].record(self._s_in)
-            comp.wait_event(self._ev_in[k])
+            comp.wait_event(self._ev_in[i])
             if i >= 2:
                 comp.wait_event(self._ev_free[k])  # the D2H of sub-batch i-2 has drained this buffer
             n_w = sub["r1"] - sub["r0"]
             if sub["grid"] is not None and n_w:
-                sub["batch"].run(self._wave[k][:n_s], lpf=self.lpf, cutoff=self.cutoff,
+                sub["batch"].run(self._wave_all[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff,
                                  windows=(sub["grid"], self.dots, self._win[k][:n_w]))
-                self._ev_wave_free[k].record(comp)
             else:
-                sub["batch"].run(self._wave[k][:n_s], lpf=self.lpf, cutoff=self.cutoff,
+                sub["batch"].run(self._wave_all[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff,
                                  out={"dec": self._dec[:max(sub["batch"].total_frames, 1)]})
-                self._ev_wave_free[k].record(comp)
                 if n_w:
                     gather_windows(self._dec, sub["base"], self.dots, 1, out=self._win[k][:n_w])
             self._ev_done[k].record(comp)
