@@ -8,14 +8,15 @@ Workload (BASELINE.json configs[1]): a synthetic
 TIMIT-TRAIN-sized corpus -- 4620 utterances, lengths U(32000, 64000) samples at 16 kHz,
 int16 white noise -- through the 128-channel ERB gammatone filterbank, the ENV1 envelope
 with the 50 Hz low-pass and the window gather on the full label grid, producing the
-(N, 11, 128) float32 input tensor.  One step = one pass of that path over the whole corpus
-shard of a rank.  Multi-GPU: utterances are independent, every rank processes its own
-corpus-sized shard with no collective (weak scaling); value = channel-samples of all ranks /
-max-over-ranks device time.
+(N, 11, 128) float32 input tensor.  One step = one pass of that path over the whole corpus.
+Multi-GPU (configs[2]): the SAME corpus, utterances dealt to the ranks by length-sorted
+round-robin (engine.shard_utterances), no collective on the data path, rows of all ranks placed
+into ONE shared host tensor (strong scaling); value = channel-samples of the corpus /
+max-over-ranks time.
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same metric
-through api.features_to_windows-style staging with HOST buffers -- pinned int16 waves H2D and
-the float32 input tensor D2H inside the timed region.  `roofline`: the fused kernel against
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, device-timed.  `e2e`: the
+same metric through the public call api.features_to_windows with HOST buffers -- pinned int16
+waves in, the float32 input tensor in host memory out, wall clock around the call.  `roofline`: the fused kernel against
 the FP32 FMA peak (80 FLOP per channel-sample), timed with CUDA events on its
 own stream inside the timed region.  `cpu_baseline`: the float64 oracle port (the reference's
 algorithm restated in C, reference Python cannot travel to the GPU box) on a bounded sample.
@@ -36,6 +37,7 @@ sys.path.insert(0, ROOT)
 FS, C, LOW, CUTOFF, RADIUS, STEP = 16000, 128, 100, 50, 5, 160
 N_UTTS, LEN_LO, LEN_HI = 4620, 32000, 64000
 FLOP_PER_CS = 80.0  # 40 FP32 FMA per channel-sample: filterbank + envelope + LPF
+TRAFFIC_1GPU = 13.710e9  # bytes per fused_kernel launch (window-store mode), profiles/r01s_ncu_final.md
 KERNELS_PER_STEP = 6  # fft cols/rows fwd, hilbert mask (+G table), fft cols/rows inv, fused (stores the windows)
 
 
@@ -45,9 +47,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances per rank (default: the config's 4620)")
+    ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances of the corpus (default: the config's 4620)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-for-bit check against the 1-GPU result")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -167,11 +170,15 @@ def main():
     from f2cnn_b200 import synth
     from f2cnn_b200.gammatone import filters
     coefs = filters.make_erb_filters(FS, filters.centre_freqs(FS, C, LOW))
-    config = {"workload": "synthetic TIMIT-TRAIN-sized corpus: %d utterances x U(%d,%d) samples @16 kHz int16, "
+    dots = 2 * RADIUS + 1
+    config = {"workload": "synthetic TIMIT-TRAIN-sized corpus: %d utterances x U(%d,%d) samples @16 kHz int16 (seed 1), "
                           "%d-ch ERB gammatone -> ENV1 (LPF %d Hz) -> (N,11,%d) float32 windows on the full label "
-                          "grid" % (args.utts, LEN_LO, LEN_HI, C, CUTOFF, C),
-              "utterances_per_gpu": args.utts, "channels": C, "lpf_hz": CUTOFF,
-              "l2": "inputs larger than L2 (rings %.1f GB per pass), no flush needed" % (args.utts * 65536 * 16 / 1e9)}
+                          "grid%s" % (args.utts, LEN_LO, LEN_HI, C, CUTOFF, C,
+                                      "" if world == 1 else "; the SAME corpus dealt to %d GPUs by length-sorted "
+                                      "round-robin, rows placed into ONE shared host tensor" % world),
+              "utterances": args.utts, "utterances_per_gpu": args.utts / world, "channels": C, "lpf_hz": CUTOFF,
+              "l2": "inputs larger than L2 (rings %.1f GB per pass and GPU), no flush needed" %
+                    (args.utts / world * 65536 * 16 / 1e9)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -181,7 +188,7 @@ def main():
         print(json.dumps({"impl": "reference", "metric": "channel-samples/sec (filterbank+envelope)",
                           "value": cb["value"], "unit": "channel-samples/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config, "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": "channel-samples/s", "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": 0}}))
@@ -195,27 +202,33 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from f2cnn_b200 import engine
+    from f2cnn_b200 import api, engine, hostmem
 
-    lengths = synth.corpus_lengths(args.utts, LEN_LO, LEN_HI, seed=1 + rank)
-    flat, offsets = synth.corpus_waves_i16(lengths, seed=1 + rank)
+    # every rank holds the SAME corpus (config 3: "same corpus utterance-sharded"); its shard is what
+    # engine.shard_utterances deals it
+    lengths = synth.corpus_lengths(args.utts, LEN_LO, LEN_HI, seed=1)
+    flat, offsets = synth.corpus_waves_i16(lengths, seed=1)
     total_samples = int(offsets[-1])
-    cs_per_step = float(C) * total_samples
+    cs_per_step = float(C) * total_samples          # the WHOLE job, whatever the number of GPUs
+    mine = engine.shard_utterances(lengths, world)[rank]
+    my_lengths = lengths[mine]
 
     plan = engine.plan_for(coefs, local_rank)
-    batch = plan.batch(lengths, step=STEP, phase=0)
+    # whole utterances (target_items=1): bit for bit what the 1-GPU pass computes, and a shard of >= 578
+    # utterances x 4 channel groups already fills the 2368 CTA slots of the device
+    batch = plan.batch(my_lengths, step=STEP, phase=0, target_items=1)
     # label grid: centres 800 + 160k, k < int(n/160 - 12): first frame of window k is frame k
-    nwin = np.maximum((lengths / STEP - (2 * RADIUS + 1) - 1).astype(np.int64), 0)
-    base = np.concatenate([batch.frame_offsets[u] + np.arange(nwin[u], dtype=np.int64) for u in range(len(lengths))])
-    n_windows = int(base.shape[0])
-    dots = 2 * RADIUS + 1
+    nwin_all = np.maximum((lengths / STEP - dots - 1).astype(np.int64), 0)
+    n_windows_all = int(nwin_all.sum())
+    nwin = nwin_all[mine]
+    n_windows = int(nwin.sum())
+    base = np.concatenate([batch.frame_offsets[u] + np.arange(nwin[u], dtype=np.int64) for u in range(len(my_lengths))])
 
     wave_host = torch.from_numpy(flat).pin_memory()
-    wave_dev = wave_host.to(dev)
+    wave_dev = torch.cat([torch.from_numpy(flat[offsets[u]:offsets[u + 1]]) for u in mine]).to(dev)
     base_dev = torch.from_numpy(base).to(dev)
     dec = torch.empty((batch.total_frames, C), dtype=torch.float32, device=dev)
     windows = torch.empty((n_windows, dots, C), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream()
 
     grid_offsets, grid_rows = batch.grid_windows(dots)
     assert grid_rows == n_windows
@@ -238,6 +251,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -252,53 +272,98 @@ def main():
     t_stop.record()
     barrier()
     clocks = sampler.stop()
-    ms_total = t_start.elapsed_ms(t_stop)
     fused_ms = float(np.mean([a.elapsed_ms(b) for a, b in ev]))
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * cs_per_step / (ms_step * 1e-3)
+    ms_step = max_over_ranks(t_start.elapsed_ms(t_stop)) / args.steps
+    value = cs_per_step / (ms_step * 1e-3)
+    windows_head = windows[:64].cpu() if rank == 0 else None
+    del windows, dec, check
 
-    # ---- e2e: host int16 waves in, host float32 input tensor out, copies inside the timed region
+    # ---- e2e: THE PUBLIC CALL, host int16 waves in, host float32 input tensor out ---------------------
     e2e = None
     if not args.no_e2e:
-        try:
-            out_host = torch.empty((n_windows, dots, C), dtype=torch.float32, pin_memory=True)
-        except RuntimeError:
-            out_host = torch.empty((n_windows, dots, C), dtype=torch.float32)
+        centers = np.concatenate([STEP * RADIUS + STEP * np.arange(k, dtype=np.int64) for k in nwin_all])
+        shard = None if world == 1 else (rank, world)
+        shared = None
+        backing = "private array (engine.host_empty: anonymous memory advised to huge pages)"
+        if world == 1:
+            out_arr = engine.host_empty((n_windows_all, dots, C), np.float32)
+        else:
+            # ONE host tensor for all ranks: a shared mapping on the RAM-backed filesystem
+            need = n_windows_all * dots * C * 4
+            d = hostmem.shm_dir()
+            if d is None or hostmem.shm_free_bytes(d) < need + (64 << 20):
+                import tempfile
+                d = tempfile.gettempdir()
+            path = os.path.join(d, "f2cnn_b200_bench_%s.f32" % os.environ.get("MASTER_PORT", "0"))
+            if rank == 0:
+                shared = hostmem.SharedArray(path, (n_windows_all, dots, C), create=True)
+            barrier()
+            if rank != 0:
+                shared = hostmem.SharedArray(path, (n_windows_all, dots, C))
+            out_arr = shared.array
+            backing = "one shared mapping under %s, mapped by all %d ranks" % (d, world)
 
-        pipe = engine.WindowPipeline(plan, lengths, [np.arange(nwin[u], dtype=np.int64) for u in range(len(lengths))],
-                                     dots=dots, step=STEP, lpf=True, cutoff=CUTOFF, n_sub=16)
-        assert pipe.n_windows == n_windows
+        def call(out):
+            return api.features_to_windows((wave_host, lengths), coefs, centers, True, CUTOFF, RADIUS, STEP,
+                                           out=out, counts=nwin_all, shard=shard)
 
-        def e2e_step():
-            pipe.run(wave_host, out_host)
-
-        for _ in range(2):
-            e2e_step()
         barrier()
-        # the pipelined host path must produce exactly what the resident path produced
-        for r0 in (0, n_windows // 2, max(n_windows - 64, 0)):
-            assert torch.equal(out_host[r0:r0 + 64], windows[r0:r0 + 64].cpu()), "e2e path differs from resident path"
+        t0 = time.perf_counter()
+        call(out_arr)                     # first call: builds and caches the pipeline, touches `out`
+        cold_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        call(out_arr)
         k = max(2, min(args.steps, 5))
-        a, b = engine.DeviceEvent(), engine.DeviceEvent()
-        a.record()
-        for _ in range(k):
-            e2e_step()
-        b.record()
         barrier()
-        ms_e2e = a.elapsed_ms(b)
-        if world > 1:
-            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
-        e2e = {"value": world * cs_per_step / (ms_e2e / k * 1e-3), "unit": "channel-samples/s",
-               "h2d_bytes_per_step": int(wave_host.numel() * 2), "d2h_bytes_per_step": int(out_host.numel() * 4),
-               "ms_per_step": ms_e2e / k, "pinned_output": bool(out_host.is_pinned()),
-               "path": "engine.WindowPipeline: %d sub-batches (the first ones smaller), H2D / compute / D2H on three streams" % len(pipe.subs)}
-        del out_host
+        t0 = time.perf_counter()
+        for _ in range(k):
+            call(out_arr)
+        torch.cuda.synchronize()
+        warm_local = (time.perf_counter() - t0) * 1e3 / k
+        barrier()
+        ms_e2e = max_over_ranks(warm_local)
+        fresh_ms = None
+        if world == 1:
+            # the same call when the caller does not hand in an output array (fresh 7.5 GB each time)
+            t0 = time.perf_counter()
+            tmp = api.features_to_windows((wave_host, lengths), coefs, centers, True, CUTOFF, RADIUS, STEP, counts=nwin_all)
+            fresh_ms = (time.perf_counter() - t0) * 1e3
+            del tmp
+        barrier()
+        verified = None
+        if rank == 0:
+            # the host path must produce exactly what the resident path produced ...
+            g0 = int(np.cumsum(nwin_all)[mine[0]] - nwin_all[mine[0]])   # first row of this rank's first utterance
+            k0 = min(64, int(nwin[0]))
+            assert np.array_equal(out_arr[g0:g0 + k0], windows_head.numpy()[:k0]), "e2e path differs from resident path"
+            if world > 1 and not args.no_verify:
+                # ... and the tensor the N ranks assembled must equal the 1-GPU result, bit for bit
+                one = api.features_to_windows((wave_host, lengths), coefs, centers, True, CUTOFF, RADIUS, STEP, counts=nwin_all)
+                verified = bool(np.array_equal(one, out_arr))
+                assert verified, "sharded result differs from the single-GPU result"
+                del one
+        barrier()
+        pipe_subs = None
+        with api._pipelines_lock:
+            for p_ in api._pipelines.values():
+                pipe_subs = (len(p_.subs), p_.placer.threads)
+        my_frames = int(np.sum((my_lengths + STEP - 1) // STEP))
+        e2e = {"value": cs_per_step / (ms_e2e * 1e-3), "unit": "channel-samples/s",
+               "h2d_bytes_per_step": total_samples * 2,
+               "d2h_bytes_per_step": int(np.sum((lengths + STEP - 1) // STEP)) * C * 4,
+               "host_tensor_bytes": n_windows_all * dots * C * 4,
+               "ms_per_step": ms_e2e, "first_call_ms": cold_ms, "fresh_output_ms": fresh_ms, "timer": "host wall clock "
+               "around the call (it returns when the last row is placed), max over ranks",
+               "path": "api.features_to_windows((pinned int16 waves, lengths), coefs, centres, LPF=True, 50, out=..., "
+                       "counts=...%s): cached engine.WindowPipeline, %s sub-batches, H2D / compute / D2H of the decimated "
+                       "frames on three streams, rows placed by %s host threads per rank" %
+                       ("" if world == 1 else ", shard=(rank, world)", pipe_subs[0] if pipe_subs else "?",
+                        pipe_subs[1] if pipe_subs else "?"),
+               "output": backing, "equals_single_gpu_result": verified, "frames_per_rank": my_frames}
+        if shared is not None:
+            barrier()
+            if rank == 0:
+                shared.unlink()
+        api.release_cached_pipelines()
 
     if rank != 0:
         if world > 1:
@@ -313,15 +378,13 @@ def main():
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     fma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s, nominal FP32 FMA at max clock
-    achieved = FLOP_PER_CS * cs_per_step / (fused_ms * 1e-3) / 1e12
+    my_cs = float(C) * float(my_lengths.sum())
+    achieved = FLOP_PER_CS * my_cs / (fused_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32_fma", "kernel": "fused_kernel", "achieved": achieved, "peak": fma_peak,
                 "unit": "TFLOP/s", "frac": achieved / fma_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one fused_kernel launch on this workload,
-                # ncu --set full capture summarised in profiles/r01s_ncu_final.md: 6.26 GB read + 7.45 GB
-                # written.  Algorithmic: 2.9 GB of ring tiles + 7.5 GB of windows = 10.4 GB; the one-warp CTAs
-                # of an utterance drift apart in time and re-read the ring tiles that have left L2 -- 4 % of
-                # HBM peak, the kernel is FMA-bound
-                "traffic": 13.710e9 if args.utts == N_UTTS else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one fused_kernel launch on the 1-GPU workload,
+                # ncu --set full capture summarised in profiles/ 
+                "traffic": TRAFFIC_1GPU if (args.utts == N_UTTS and world == 1) else None,
                 "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has no FP32 entry); "
                                "tools/fma_peak.cu measured 73.8 TFLOP/s sustained (FFMA2) on this pool",
                 "kernel_ms": fused_ms, "kernel_share_of_step": fused_ms / ms_step,
@@ -329,16 +392,16 @@ def main():
                 # ring tiles (x, xi, G: 12 B per sample, shared by the C channels) + every decimated frame
                 # stored into the 2R+1 window rows that contain it
                 "hbm": {"algorithmic_bytes_per_channel_sample": 12.0 / C + 4.0 * dots / STEP,
-                        "achieved_GBps": (12.0 / C + 4.0 * dots / STEP) * cs_per_step / (fused_ms * 1e-3) / 1e9,
+                        "achieved_GBps": (12.0 / C + 4.0 * dots / STEP) * my_cs / (fused_ms * 1e-3) / 1e9,
                         "peak_GBps": peaks.get("hbm_gbs")}}
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         cpu, _ = cpu_arm(coefs, lengths, 1, args.cpu_seconds)
     out = {"metric": "channel-samples/sec (filterbank+envelope)", "value": value, "unit": "channel-samples/s",
            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps,
-           "roofline": roofline, "cpu_baseline": cpu, "windows_per_step": n_windows * world}
+           "roofline": roofline, "cpu_baseline": cpu, "windows_per_step": n_windows_all}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -12,7 +12,8 @@ LIB_PATH = os.environ.get("F2CNN_B200_LIB") or os.path.join(_HERE, "libf2cnn_b20
 F2_OK = 0
 F2_I16, F2_F32, F2_F64 = 0, 1, 2
 F2_ROWS_ENVELOPE, F2_ROWS_HILBERT, F2_ROWS_LOWPASS = 0, 1, 2
-ABI_VERSION = 5
+F2_ERR_INVALID, F2_ERR_CUDA, F2_ERR_WORKSPACE, F2_ERR_UNSUPPORTED, F2_ERR_INDEX = 1, 2, 3, 4, 5
+ABI_VERSION = 6
 
 
 class F2Error(RuntimeError):
@@ -22,7 +23,9 @@ class F2Error(RuntimeError):
 
 
 class RunArgs(ctypes.Structure):
+    """struct f2_run_args; struct_size is filled in by __init__ (the library rejects short structs)."""
     _fields_ = [
+        ("struct_size", ctypes.c_uint32),
         ("wave", ctypes.c_void_p),
         ("wave_dtype", ctypes.c_int),
         ("lpf", ctypes.c_int),
@@ -39,6 +42,15 @@ class RunArgs(ctypes.Structure):
         ("win_offsets", ctypes.c_void_p),
         ("win_dots", ctypes.c_int),
     ]
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.struct_size = ctypes.sizeof(RunArgs)
+
+
+class WinRun(ctypes.Structure):
+    """struct f2_win_run: `count` windows, window i = frames first_frame+i .. +dots-1 -> row row0+i."""
+    _fields_ = [("first_frame", ctypes.c_int64), ("row0", ctypes.c_int64), ("count", ctypes.c_int64)]
 
 
 _lib = None
@@ -82,6 +94,22 @@ SIGNATURES = {
                                        ctypes.c_void_p]),
     "f2_label_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "f2_window_runs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_int), ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "f2_place_windows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_int]),
+    "f2_placer_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "f2_placer_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "f2_placer_threads": (ctypes.c_int, [ctypes.c_void_p]),
+    "f2_placer_submit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "f2_placer_wait": (ctypes.c_int, [ctypes.c_void_p]),
+    "f2_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "f2_host_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "f2_upload_spans": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "f2_event_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
     "f2_event_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "f2_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -3,6 +3,10 @@
 Each function stages its inputs through pinned host memory, launches the C-ABI sequence on
 the current CUDA stream and returns freshly allocated numpy arrays of the reference's dtype
 and layout.  All arithmetic happens in libf2cnn_b200.so."""
+import hashlib
+import threading
+from collections import OrderedDict
+
 import numpy as np
 import torch
 
@@ -141,14 +145,55 @@ def window_indices(n, centers, radius, step):
     return idx
 
 
-def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=5, step=160, device_out=False):
+_pipelines = OrderedDict()   # corpus-sized requests: cached engine.WindowPipeline objects
+_pipelines_lock = threading.Lock()
+_MAX_PIPELINES = 2
+
+
+def _pipeline_for(plan, lengths, dots, step, phase, LPF, CUTOFF, src_offsets=None, share=1):
+    """The sub-batch layout, device buffers, pinned staging and worker pool of a corpus-sized request
+    depend only on the utterance lengths and the grid: built once, reused by every later call with the
+    same corpus (a second `prepare input --cutoff K` run, the next epoch's noise draw, a benchmark)."""
+    key = (id(plan), hashlib.sha1(lengths.tobytes()).hexdigest(), int(dots), int(step), int(phase), int(share),
+           None if src_offsets is None else hashlib.sha1(np.ascontiguousarray(src_offsets).tobytes()).hexdigest())
+    with _pipelines_lock:
+        pipe = _pipelines.get(key)
+        if pipe is None:
+            # `share` processes of this box run a pipeline each: split the host cores between their pools
+            threads = max(1, engine.host_cores() // max(int(share), 1))
+            pipe = engine.WindowPipeline(plan, lengths, dots=dots, step=step, phase=phase, lpf=LPF, cutoff=CUTOFF,
+                                         src_offsets=src_offsets, placer=engine.Placer(threads))
+            _pipelines[key] = pipe
+            while len(_pipelines) > _MAX_PIPELINES:
+                _pipelines.popitem(last=False)
+        else:
+            _pipelines.move_to_end(key)
+        pipe.lpf, pipe.cutoff = bool(LPF), CUTOFF
+        return pipe
+
+
+def release_cached_pipelines():
+    """Drop the cached corpus pipelines (device buffers, pinned staging, worker threads)."""
+    with _pipelines_lock:
+        _pipelines.clear()
+
+
+def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=5, step=160, device_out=False,
+                        out=None, counts=None, shard=None):
     """Fused path from waveforms to the (N, 2R+1, C) float32 input tensor.
 
     waves: list of 1-D arrays (same dtype), or (flat, lengths) as returned by ingest.read_corpus
     (one buffer of all samples, pinned for full speed); timepoints: list of int arrays (window
-    centres per utterance, in output order).  Equivalent to erb_filterbank ->
-    ExtractEnvelopeFromMatrix(LPF, CUTOFF) -> the gather of InputGenerator.py:73-80 per
-    utterance, rows concatenated in list order."""
+    centres per utterance, in output order) -- or, with `counts`, ONE flat int array of all centres
+    and counts[u] of them per utterance.  Equivalent to
+    erb_filterbank -> ExtractEnvelopeFromMatrix(LPF, CUTOFF) -> the gather of
+    InputGenerator.py:73-80 per utterance, rows concatenated in list order.  `out`: an existing
+    C-contiguous (N, 2R+1, C) float32 numpy array to fill (a corpus-sized result is 7.5 GB: reusing
+    it saves its page faults); by default a fresh array is returned.
+    shard=(rank, world): one of `world` processes (one per GPU, e.g. under torchrun) that were all
+    handed the SAME corpus and the SAME `out` -- a shared mapping, hostmem.SharedArray.  This call
+    computes the utterances engine.shard_utterances deals to `rank` and writes their rows, and only
+    theirs, at their final offsets; there is nothing to exchange afterwards."""
     coefs = np.asarray(coefs, dtype=np.float64)
     plan = engine.plan_for(coefs)
     C = plan.n_channels
@@ -169,27 +214,68 @@ def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=
             waves = [w.astype(np.float64) for w in waves]
         lengths = np.asarray([w.shape[0] for w in waves], dtype=np.int64)
         n_utts = len(waves)
-    idx = [window_indices(int(n), tp, radius, step) for n, tp in zip(lengths, timepoints)]
-    total = int(sum(i.shape[0] for i in idx))
+    if counts is not None:
+        centers = np.ascontiguousarray(timepoints, dtype=np.int64).reshape(-1)
+        counts = np.ascontiguousarray(counts, dtype=np.int64).reshape(-1)
+        if counts.shape[0] != n_utts or int(counts.sum()) != centers.shape[0]:
+            raise ValueError("counts: one entry per utterance, adding up to the number of timepoints")
+    else:
+        if len(timepoints) != n_utts:
+            raise ValueError("%d utterances, %d timepoint lists" % (n_utts, len(timepoints)))
+        counts = np.fromiter((len(t) for t in timepoints), dtype=np.int64, count=n_utts)
+        centers = (np.concatenate([np.asarray(t, dtype=np.int64).reshape(-1) for t in timepoints])
+                   if n_utts else np.zeros(0, dtype=np.int64))
+    total = int(counts.sum())
+    if out is not None:
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and
+                out.shape == (total, dots, C)):
+            raise ValueError("out must be a C-contiguous float32 array of shape %s" % ((total, dots, C),))
+        if device_out:
+            raise ValueError("out= is a host array; it cannot be combined with device_out")
+    if shard is not None:
+        rank, world = int(shard[0]), int(shard[1])
+        if out is None or device_out or not 0 <= rank < world:
+            raise ValueError("shard=(rank, world) needs 0 <= rank < world and the shared `out` array")
     if total == 0:
-        return np.zeros((0, dots, C), dtype=np.float32)
+        return np.zeros((0, dots, C), dtype=np.float32) if out is None else out
+
+    if shard is not None or (not device_out and total * dots * C * 4 >= _PIPELINE_BYTES and n_utts >= 8):
+        # corpus-sized request: decimated frames over PCIe, rows placed on the host (engine.WindowPipeline)
+        first = int(centers[0]) - radius * step
+        phase = first % step if first >= 0 else 0
+        sel, src_offsets, row_offsets, share = slice(None), None, None, 1
+        cen, lens, cnts = centers, lengths, counts
+        if shard is not None:
+            sel = engine.shard_utterances(lengths, world)[rank]
+            mine = np.zeros(n_utts, dtype=bool)
+            mine[sel] = True
+            cen, lens, cnts = centers[np.repeat(mine, counts)], lengths[sel], counts[sel]
+            src_offsets = (np.cumsum(lengths) - lengths)[sel]
+            row_offsets = (np.cumsum(counts) - counts)[sel]
+            share = world
+        n_dec = np.where(lens > phase, (lens - phase + step - 1) // step, 0)
+        frame_offsets = np.concatenate([[0], np.cumsum(n_dec)]).astype(np.int64)
+        runs, phase2, _ = engine.window_runs(cen, cnts, lens, frame_offsets, radius, step, phase, row_offsets=row_offsets)
+        if runs is not None and phase2 == phase:
+            pipe = _pipeline_for(plan, lens, dots, step, phase, LPF, CUTOFF, src_offsets, share)
+            result = engine.host_empty((total, dots, C), np.float32) if out is None else out
+            if flat_in is not None:
+                pipe.run(flat_in, runs, result)
+            else:
+                pipe.run(waves if shard is None else [waves[u] for u in sel], runs, result)
+            return result
+        if shard is not None:
+            raise ValueError("shard= needs timepoints that are windows of consecutive frames of one decimated grid")
+
+    # general path: one batch, windows gathered on the device
+    cpos = np.concatenate([[0], np.cumsum(counts)])
+    idx = [window_indices(int(n), centers[cpos[u]:cpos[u + 1]], radius, step) for u, n in enumerate(lengths)]
     # one decimated grid serves every window when all indices share a residue mod step
     allidx = np.concatenate([i.reshape(-1) for i in idx if i.size])
     phase = int(allidx[0] % step)
     on_grid = bool(np.all(allidx % step == phase))
     if flat_in is None:
         flat_in = torch.from_numpy(np.concatenate(waves) if len(waves) > 1 else waves[0])
-    strided = on_grid and all(bool(np.all(np.diff(i, axis=1) == step)) for i in idx if i.size)
-    if strided and not device_out and total * dots * C * 4 >= _PIPELINE_BYTES and n_utts >= 8:
-        # corpus-sized request: overlap H2D / compute / D2H over sub-batches (PCIe-bound path)
-        bases = [(i[:, 0] - phase) // step if i.size else np.zeros(0, dtype=np.int64) for i in idx]
-        pipe = engine.WindowPipeline(plan, lengths, bases, dots=dots, step=step, phase=phase, lpf=LPF, cutoff=CUTOFF,
-                                     n_sub=max(2, min(16, n_utts // 64)))
-        wave_host = flat_in if flat_in.is_pinned() else flat_in.pin_memory()
-        out_host = torch.empty((total, dots, C), dtype=torch.float32, pin_memory=True)
-        pipe.run(wave_host, out_host)
-        torch.cuda.current_stream().synchronize()
-        return out_host.numpy()
     wave_dev = (flat_in if flat_in.is_pinned() or flat_in.numel() * flat_in.element_size() < (1 << 16)
                 else flat_in.pin_memory()).to(plan.device, non_blocking=True)
     if on_grid:
@@ -205,17 +291,23 @@ def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=
         rows = np.concatenate(bases)
         if strided:
             base_dev = _to_device(np.ascontiguousarray(rows[:, 0]), plan.device)
-            out = engine.gather_windows(res["dec"], base_dev, dots, 1)
+            res_w = engine.gather_windows(res["dec"], base_dev, dots, 1)
         else:
-            out = engine.gather_index(res["dec"], _to_device(np.ascontiguousarray(rows.reshape(-1)), plan.device))
-            out = out.view(total, dots, C)
+            res_w = engine.gather_index(res["dec"], _to_device(np.ascontiguousarray(rows.reshape(-1)), plan.device))
+            res_w = res_w.view(total, dots, C)
     else:
         batch = plan.batch(lengths, step=step, phase=0)
         res = batch.run(wave_dev, lpf=LPF, cutoff=CUTOFF, env_t=True)
         rows = np.concatenate([i + batch.sample_offsets[u] for u, i in enumerate(idx) if i.size])
-        out = engine.gather_index(res["env_t"], _to_device(np.ascontiguousarray(rows.reshape(-1)), plan.device))
-        out = out.view(total, dots, C)
-    return out if device_out else _to_host(out)
+        res_w = engine.gather_index(res["env_t"], _to_device(np.ascontiguousarray(rows.reshape(-1)), plan.device))
+        res_w = res_w.view(total, dots, C)
+    if device_out:
+        return res_w
+    host = _to_host(res_w)
+    if out is not None:
+        out[...] = host
+        return out
+    return host
 
 
 def dense_frames(wave, coefs, LPF=False, CUTOFF=100, radius=5, step=160, normalize=True, dtype=np.float64,
@@ -229,7 +321,9 @@ def dense_frames(wave, coefs, LPF=False, CUTOFF=100, radius=5, step=160, normali
     n = int(w.shape[0])
     dots = 2 * radius + 1
     nb = int(n - dots * step)
-    i0, i1 = (0, nb) if frames is None else frames
+    i0, i1 = (0, nb) if frames is None else (int(frames[0]), int(frames[1]))
+    if frames is not None and not (0 <= i0 <= i1 <= max(nb, 0)):
+        raise IndexError("frames=(%d, %d) outside the %d frames of this utterance" % (i0, i1, max(nb, 0)))
     if nb <= 0 or i1 <= i0:
         return np.zeros((0, dots, plan.n_channels), dtype=dtype)
     batch = plan.batch([n], step=step)

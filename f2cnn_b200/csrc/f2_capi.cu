@@ -15,7 +15,6 @@
 #include "f2_edge.cuh"
 #include "f2_fused.cuh"
 #include "f2_label.cuh"
-#include "f2_lanes.cuh"
 #include "f2_post.cuh"
 #include "f2_prep.cuh"
 
@@ -82,6 +81,15 @@ void butter1(double cutoff_hz, double* b0, double* a1) {
 
 }  // namespace
 
+// error channel of the other translation units of the library (f2_host.cpp); not exported
+extern "C" int f2_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 struct f2_plan {
     int device = 0;
     int C = 0;
@@ -96,14 +104,6 @@ struct f2_plan {
 
 struct f2_batch {
     f2_plan* plan = nullptr;
-    // lane-stream decomposition (decimated-output path)
-    std::vector<f2::LaneStream> streams;
-    std::vector<char> group_from_zero;  // every stream of the group starts at t0 == 0
-    f2::LaneStream* d_streams = nullptr;
-    f2::LaneGroup* d_groups = nullptr;
-    int n_groups = 0;
-    int groups_w_lpf = -1;  // low-pass warm-up the uploaded group table was built for
-    bool lanes_ok = false;
     int n_utts = 0;
     int step = 1, phase = 0;
     std::vector<f2::UttDesc> utts;
@@ -124,7 +124,7 @@ struct f2_batch {
 extern "C" {
 
 const char* f2_last_error(void) { return g_err; }
-int f2_abi_version(void) { return 5; }
+int f2_abi_version(void) { return 6; }
 
 int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1) {
     if (!b0 || !a1 || !(cutoff_hz > 0.0) || !(cutoff_hz < 8000.0))
@@ -344,7 +344,6 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
             for (int cb = 0; cb < cblocks; ++cb) seg_of[(size_t)cb] = direct[(size_t)cb] ? sd : sD;
         }
     }
-    if (target_items <= 0) target_items = 4 * wave_ctas;  // lane-stream decomposition below
     auto build_items = [&](const std::vector<long long>& segs, bool same_for_all) {
         std::vector<f2::Item> out;
         auto push = [&](int u, int cb, long long t0, long long len, int n) {
@@ -391,58 +390,6 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
     b->n_items_uniform = (long long)items_uniform.size();
     b->n_whole = whole / units * cblocks;  // same utterance count, in CTAs
 
-    // ---- lane streams: (utterance, time chunk), 32 per CTA, kLaneWarps channels per CTA ------
-    {
-        const int tile = f2::lane_tile_samples();
-        const int cb8 = (plan->C + f2::kLaneWarps - 1) / f2::kLaneWarps;
-        long long whole8 = 0;
-        bool sizes_ok = plan->C <= f2::kMaxConstChan;
-        for (int u = 0; u < n_utts; ++u) {
-            if (lengths[u] <= 0) continue;
-            whole8 += cb8;
-            if (b->utts[(size_t)u].N2 < tile) sizes_ok = false;  // ring shorter than a tile
-        }
-        // chunk boundaries on multiples of lcm(tile, step) keep the decimated stores of the
-        // lanes of a warp aligned in time
-        long long align = tile;
-        {
-            long long a = tile, c = step;
-            while (c) { long long r = a % c; a = c; c = r; }
-            const long long l = (long long)tile / a * step;
-            if (l <= 4096) align = l;
-        }
-        long long seg8 = (long long)1 << 40;
-        const long long target_ctas = target_items;  // same meaning: CTAs wanted
-        // split only when whole utterances give less than half the CTAs wanted
-        if (((whole8 / cb8 + 31) / 32) * cb8 * 2 < target_ctas && wave > 0) {
-            // CTAs = ceil(streams/32) * cb8: ask for about target_ctas of them
-            const long long want_streams = std::max<long long>(32, target_ctas * 32 / cb8);
-            seg8 = (long long)align_up((size_t)std::max<long long>(wave / want_streams, 2048), (size_t)align);
-        }
-        for (int u = 0; u < n_utts; ++u) {
-            const int n = b->utts[(size_t)u].n;
-            if (n <= 0) continue;
-            const long long nseg = std::max<long long>(1, (n + seg8 - 1) / seg8);
-            const long long len = (long long)align_up((size_t)((n + nseg - 1) / nseg), (size_t)align);
-            for (long long t0 = 0; t0 < n; t0 += len) {
-                f2::LaneStream st;
-                st.utt = u;
-                st.t0 = (int)t0;
-                st.t1 = (int)std::min<long long>(n, t0 + len);
-                st.pad = 0;
-                b->streams.push_back(st);
-            }
-        }
-        std::stable_sort(b->streams.begin(), b->streams.end(), [](const f2::LaneStream& a, const f2::LaneStream& c) {
-            return (a.t1 - a.t0) > (c.t1 - c.t0);
-        });
-        b->n_groups = (int)((b->streams.size() + 31) / 32);
-        b->group_from_zero.assign((size_t)b->n_groups, 1);
-        for (size_t i = 0; i < b->streams.size(); ++i)
-            if (b->streams[i].t0 != 0) b->group_from_zero[i / 32] = 0;
-        b->lanes_ok = sizes_ok && !b->streams.empty();
-    }
-
     DeviceGuard guard(plan->device);
     cudaError_t e = cudaSuccess;
     if (n_utts > 0) {
@@ -461,19 +408,10 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
                                cudaMemcpyHostToDevice);
         }
     }
-    if (e == cudaSuccess && b->lanes_ok) {
-        e = cudaMalloc(&b->d_streams, sizeof(f2::LaneStream) * b->streams.size());
-        if (e == cudaSuccess)
-            e = cudaMemcpy(b->d_streams, b->streams.data(), sizeof(f2::LaneStream) * b->streams.size(),
-                           cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMalloc(&b->d_groups, sizeof(f2::LaneGroup) * (size_t)b->n_groups);
-    }
     if (e != cudaSuccess) {
         if (b->d_utts) cudaFree(b->d_utts);
         if (b->d_items) cudaFree(b->d_items);
         if (b->d_items_uniform) cudaFree(b->d_items_uniform);
-        if (b->d_streams) cudaFree(b->d_streams);
-        if (b->d_groups) cudaFree(b->d_groups);
         delete b;
         return fail(F2_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e));
     }
@@ -487,8 +425,6 @@ int f2_batch_destroy(f2_batch* batch) {
     if (batch->d_utts) cudaFree(batch->d_utts);
     if (batch->d_items) cudaFree(batch->d_items);
     if (batch->d_items_uniform) cudaFree(batch->d_items_uniform);
-    if (batch->d_streams) cudaFree(batch->d_streams);
-    if (batch->d_groups) cudaFree(batch->d_groups);
     delete batch;
     return F2_OK;
 }
@@ -523,6 +459,10 @@ size_t f2_batch_workspace_bytes(const f2_batch* b, int want_full_gfb, int want_f
 
 int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t workspace_bytes, void* stream_) {
     if (!b || !a) return fail(F2_ERR_INVALID, "f2_batch_run: null batch/args");
+    if (a->struct_size < sizeof(f2_run_args))
+        return fail(F2_ERR_INVALID, "f2_batch_run: f2_run_args.struct_size is %u, this library (ABI %d) needs %zu -- "
+                    "the caller was built against an older include/f2cnn_b200.h", a->struct_size, f2_abi_version(),
+                    sizeof(f2_run_args));
     if (b->total_samples == 0) return F2_OK;
     if (!a->wave || a->wave_dtype < F2_I16 || a->wave_dtype > F2_F64)
         return fail(F2_ERR_INVALID, "f2_batch_run: wave pointer/dtype");
@@ -584,61 +524,6 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     hp.min_log2N2 = b->min_log2;
     hp.max_log2N2 = b->max_log2;
     F2_CUDA(f2::launch_prep(pp, hp, stream));
-
-    // ---- decimated output only: lane-stream kernel (warp-uniform coefficients) --------------
-    // Experimental (off by default, F2_USE_LANES=1): measured equal to the thread-per-channel
-    // kernel (47.6 vs 47.0 ms on config 2) because ptxas keeps only a third of the coefficients
-    // on the uniform datapath and the per-warp code copies press on the instruction cache.
-    const bool use_lanes = getenv("F2_USE_LANES") != nullptr;
-    if (b->lanes_ok && use_lanes && a->dec && !a->gfb && !a->env && !a->env_t) {
-        static long long const_owner[64] = {0};
-        const int dev = plan->device;
-        if (dev < 64 && const_owner[dev] != plan->id) {
-            F2_CUDA(f2::upload_lane_constants(plan->h_chan.data(), plan->c_pad, stream));
-            const_owner[dev] = plan->id;
-        } else if (dev >= 64) {
-            F2_CUDA(f2::upload_lane_constants(plan->h_chan.data(), plan->c_pad, stream));
-        }
-        const int tile = f2::lane_tile_samples();
-        const int w_lpf = a->lpf ? (int)align_up((size_t)ceil(log(1e-7) / log(-a1)), (size_t)tile) : 0;
-        if (b->groups_w_lpf != w_lpf) {
-            std::vector<f2::LaneGroup> groups((size_t)b->n_groups);
-            const int w_cold = std::max(plan->w_imag, plan->w_casc);
-            for (int g = 0; g < b->n_groups; ++g) {
-                if (b->group_from_zero[(size_t)g]) {
-                    groups[(size_t)g].mA = groups[(size_t)g].mB = plan->w_imag / tile;  // exact start at t = 0
-                } else {
-                    groups[(size_t)g].mA = w_cold / tile;
-                    groups[(size_t)g].mB = (w_cold + w_lpf) / tile;
-                }
-            }
-            F2_CUDA(cudaMemcpyAsync(b->d_groups, groups.data(), sizeof(f2::LaneGroup) * groups.size(),
-                                    cudaMemcpyHostToDevice, stream));
-            F2_CUDA(cudaStreamSynchronize(stream));  // `groups` is a host temporary
-            b->groups_w_lpf = w_lpf;
-        }
-        F2_CUDA(f2::launch_edge(b->d_utts, b->n_utts, plan->d_chan, plan->C, plan->c_pad, xz, plan->w_edge, edge,
-                                stream));
-        f2::LaneParams lp;
-        lp.utts = b->d_utts;
-        lp.streams = b->d_streams;
-        lp.groups = b->d_groups;
-        lp.n_streams = (int)b->streams.size();
-        lp.xz = xz;
-        lp.G = G;
-        lp.edge = edge;
-        lp.dec = a->dec;
-        lp.C = plan->C;
-        lp.step = b->step;
-        lp.phase = b->phase;
-        lp.lpf = a->lpf ? 1 : 0;
-        lp.lp_k = (float)(-a1);
-        lp.lp_b0 = (float)b0;
-        if (a->ev_fused_start) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_start, stream));
-        F2_CUDA(f2::launch_lanes(lp, b->n_groups, stream));
-        if (a->ev_fused_stop) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_stop, stream));
-        return F2_OK;
-    }
 
     f2::FusedParams fp;
     fp.utts = b->d_utts;
@@ -790,6 +675,20 @@ int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64
     F2_CUDA(f2::launch_prep(pp, hp, stream));
     F2_CUDA(f2::launch_rows_envelope(d_rows, (int)r.rows_pad, xz, op, lpf ? 1 : 0, (float)(-a1), (float)b0, out,
                                      out_dtype, stream));
+    return F2_OK;
+}
+
+int f2_upload_spans(void* dst_device, const void* src_host, const int64_t* src_off, const int64_t* dst_off,
+                    const int64_t* nbytes, int64_t n_spans, void* stream) {
+    if (n_spans == 0) return F2_OK;
+    if (!dst_device || !src_host || !src_off || !dst_off || !nbytes || n_spans < 0)
+        return fail(F2_ERR_INVALID, "f2_upload_spans: bad arguments");
+    for (int64_t i = 0; i < n_spans; ++i) {
+        if (nbytes[i] < 0 || src_off[i] < 0 || dst_off[i] < 0) return fail(F2_ERR_INVALID, "f2_upload_spans: span %lld is negative", (long long)i);
+        if (nbytes[i] == 0) continue;
+        F2_CUDA(cudaMemcpyAsync((char*)dst_device + dst_off[i], (const char*)src_host + src_off[i], (size_t)nbytes[i],
+                                cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    }
     return F2_OK;
 }
 

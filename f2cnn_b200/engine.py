@@ -53,7 +53,9 @@ class Plan:
         self._h = ctypes.c_void_p()
         check(_native.lib().f2_plan_create(coefs.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), self.n_channels,
                                            self.device.index, ctypes.byref(self._h)))
-        self._ws = None
+        self._ws = {}
+        self._ws_lock = threading.Lock()
+        self._frozen = False  # plan_for() hands the same object to every caller: no mutation there
 
     def __del__(self):
         try:
@@ -65,6 +67,10 @@ class Plan:
             pass
 
     def set_warmup(self, w_imag=0, w_edge=0, w_casc=0):
+        """Development knob (f2_plan_set_warmup).  Only on a plan you created yourself with Plan(...):
+        the plans plan_for() caches are shared by every caller and stay as created."""
+        if self._frozen:
+            raise RuntimeError("set_warmup on a cached plan (engine.plan_for): create a private engine.Plan(coefs)")
         check(_native.lib().f2_plan_set_warmup(self._h, int(w_imag), int(w_edge), int(w_casc)))
 
     def get_warmup(self):
@@ -75,12 +81,22 @@ class Plan:
     def batch(self, lengths, step=160, phase=0, target_items=0):
         return Batch(self, lengths, step, phase, target_items)
 
-    def workspace(self, nbytes):
-        """Grow-only scratch shared by this plan's launches (caller-owned per the C ABI)."""
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._ws
+    def workspace(self, nbytes, stream=None):
+        """Grow-only scratch of this plan's launches ON ONE STREAM (caller-owned per the C ABI).
+        Launches on different streams get different blocks, so they may overlap; the block is
+        allocated under the stream it serves, which is what makes handing a replaced block back to
+        torch's caching allocator safe (it is only reused in that stream's order)."""
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        key = int(s.cuda_stream)
+        with self._ws_lock:
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < nbytes:
+                self._ws.pop(key, None)
+                ws = None
+                with torch.cuda.stream(s):
+                    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+                self._ws[key] = ws
+            return ws
 
     # -- stand-alone envelope of matrix rows (ExtractEnvelopeFromMatrix on foreign data) ----
     def envelope_rows(self, matrix_dev, lpf, cutoff, out_dtype=torch.float64, stream=None, op=0):
@@ -89,7 +105,9 @@ class Plan:
         if rows == 0 or n == 0:
             return out
         L = _native.lib()
-        ws = self.workspace(L.f2_envelope_rows_workspace_bytes(rows, n))
+        if not matrix_dev.is_contiguous() or matrix_dev.device != self.device:
+            raise ValueError("envelope_rows wants a contiguous matrix on the plan's device")
+        ws = self.workspace(L.f2_envelope_rows_workspace_bytes(rows, n), stream)
         check(L.f2_rows_op(self._h, _ptr(matrix_dev), _T2F2[matrix_dev.dtype], rows, n, int(op), int(bool(lpf)),
                            float(cutoff), _ptr(out), _T2F2[out_dtype], _ptr(ws), ws.numel(), _stream_ptr(stream)))
         return out
@@ -115,6 +133,7 @@ class Batch:
         self.sample_offsets = np.zeros(self.n_utts + 1, dtype=np.int64)
         np.cumsum(self.lengths, out=self.sample_offsets[1:])
         self._grid = {}
+        self._grid_rows = {}
 
     def __del__(self):
         try:
@@ -137,6 +156,7 @@ class Batch:
             nb = np.maximum(self.lengths // self.step - key - 1, 0)
             off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
             self._grid[key] = (torch.from_numpy(off).to(self.plan.device), int(off[-1]))
+            self._grid_rows[int(self._grid[key][0].data_ptr())] = int(off[-1])
         return self._grid[key]
 
     def run(self, wave_dev, lpf=False, cutoff=100, gfb=None, env=None, env_t=False, dec=False, stream=None,
@@ -154,7 +174,18 @@ class Batch:
             raise ValueError("wave has %d samples, batch expects %d" % (wave_dev.numel(), self.total_samples))
         if wave_dev.device != plan.device:
             raise ValueError("wave is on %s, plan on %s" % (wave_dev.device, plan.device))
+        if not wave_dev.is_contiguous() or wave_dev.dtype not in _T2F2:
+            raise ValueError("wave must be a contiguous int16 / float32 / float64 tensor")
         res = {} if out is None else dict(out)
+        # the C ABI takes bare pointers: whatever the caller preallocated is checked here
+        want = {"gfb": (C * self.total_samples, (torch.float32, torch.float64)),
+                "env": (C * self.total_samples, (torch.float32, torch.float64)),
+                "env_t": (C * self.total_samples, (torch.float32,)), "dec": (C * self.total_frames, (torch.float32,))}
+        for key, (numel, dts) in want.items():
+            t = res.get(key)
+            if t is not None and (t.numel() < numel or t.dtype not in dts or not t.is_contiguous() or
+                                  t.device != plan.device):
+                raise ValueError("preallocated %r: need >= %d contiguous elements of %s on %s" % (key, numel, dts, plan.device))
         if gfb is not None and "gfb" not in res:
             res["gfb"] = torch.empty(C * self.total_samples, dtype=gfb, device=plan.device)
         if env is not None and "env" not in res:
@@ -184,15 +215,23 @@ class Batch:
             if len(windows) > 2 and windows[2] is not None:
                 res["windows"] = windows[2]
             elif "windows" not in res:
-                res["windows"] = torch.empty((int(offs[-1].item()), dots, C), dtype=torch.float32, device=plan.device)
+                rows = self._grid_rows.get(int(offs.data_ptr()))
+                rows = int(offs[-1].item()) if rows is None else rows
+                res["windows"] = torch.empty((rows, dots, C), dtype=torch.float32, device=plan.device)
             w = res["windows"]
             if w.dtype != torch.float32 or not w.is_contiguous() or w.device != plan.device:
                 raise ValueError("windows output: contiguous float32 tensor on the plan's device")
+            rows = self._grid_rows.get(int(offs.data_ptr()))
+            if rows is None:  # offsets that did not come from grid_windows(): one small D2H read
+                rows = int(offs[-1].item())
+            if w.numel() < rows * dots * C:
+                raise ValueError("windows output holds %d floats, the offsets ask for %d rows x %d x %d" %
+                                 (w.numel(), rows, dots, C))
             a.windows, a.win_offsets, a.win_dots = w.data_ptr(), offs.data_ptr(), dots
         if fused_events is not None:  # (DeviceEvent, DeviceEvent) around the fused kernel
             a.ev_fused_start, a.ev_fused_stop = fused_events[0].handle, fused_events[1].handle
         need = self.workspace_bytes(g is not None, e is not None and "env_t" not in res)
-        ws = plan.workspace(need)
+        ws = plan.workspace(need, stream)
         check(_native.lib().f2_batch_run(self._h, ctypes.byref(a), _ptr(ws), ws.numel(), _stream_ptr(stream)))
         return res
 
@@ -279,139 +318,242 @@ def label_fit(formant_dev, first_dev, center_dev, dots, step, stream=None):
     return out
 
 
+def shard_utterances(lengths, world):
+    """Length-sorted round-robin deal of utterances over `world` devices (the
+    reference's unit of parallelism is the file, GammatoneFiltering.py:121-125): sort by length,
+    longest first, and deal like cards, so that every shard sees the same length distribution and
+    sum(n_u) differs by at most one utterance.  Returns `world` ascending index arrays."""
+    lengths = np.asarray(lengths, dtype=np.int64).reshape(-1)
+    world = max(1, int(world))
+    order = np.argsort(-lengths, kind="stable")
+    return [np.sort(order[r::world]) for r in range(world)]
+
+
+def host_cores():
+    """Cores this process may run on (cgroup / affinity aware)."""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def _pinned_empty(n, dtype):
+    return torch.empty(max(int(n), 1), dtype=dtype, pin_memory=True)
+
+
 class WindowPipeline:
-    """Host waves in, host (N, 2R+1, C) float32 windows out, for a whole corpus.
+    """Host waves in, host (N, 2R+1, C) float32 windows out, for a whole corpus (or one shard of it).
 
-    The utterances are cut into `n_sub` contiguous sub-batches; while sub-batch i is being
-    filtered on the compute stream, the windows of sub-batch i-1 travel to the host on a copy
-    stream (double-buffered device output); the waves of all sub-batches are uploaded on a third
-    stream right at the start (2 bytes per sample).  PCIe is the bottleneck of this path (the window tensor is 11x the decimated
-    envelope), so hiding the 50-odd ms of compute behind the D2H copy is what matters.
+    The input tensor of the reference is (2R+1)x redundant -- row k of an utterance is 2R+1
+    consecutive decimated frames -- so the DECIMATED FRAMES travel over PCIe (0.68 GB for the
+    4620-utterance corpus instead of 7.5 GB) and the rows are placed on the host by the worker pool
+    of f2_host.cpp.  The utterances are cut into sub-batches: the waves of all of them are queued
+    on an upload stream at the start, sub-batch i is filtered on the compute stream while the
+    frames of sub-batch i-1 travel on a download stream, and each download is followed, in stream
+    order, by the host placement of its rows (cudaLaunchHostFunc -> thread pool), so the host
+    never waits between sub-batches.
 
-    bases[u]: int64 array, for every window of utterance u the index (within the utterance)
-    of its FIRST decimated frame; windows are `dots` consecutive frames (on-grid labels)."""
+    lengths[u]: samples of utterance u; src_offsets[u]: where it starts in the host buffer passed
+    to run() (default: back to back), so a shard can read its utterances out of the buffer that
+    holds the whole corpus.  Frames are numbered over the pipeline's utterances in order
+    (`frame_offsets`), which is what engine.window_runs wants."""
 
-    def __init__(self, plan, lengths, bases, dots=11, step=160, phase=0, lpf=True, cutoff=50, n_sub=8):
+    def __init__(self, plan, lengths, dots=11, step=160, phase=0, lpf=True, cutoff=50, n_sub=16, src_offsets=None,
+                 placer=None):
         self.plan, self.dots, self.lpf, self.cutoff = plan, int(dots), bool(lpf), cutoff
-        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        self.step, self.phase = int(step), int(phase)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(-1)
+        self.lengths = lengths
         U = int(lengths.shape[0])
-        n_sub = max(1, min(int(n_sub), U))
-        cum = np.concatenate([[0], np.cumsum(lengths)])
-        # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that: the
-        # D2H copy -- the bottleneck -- cannot start before the first sub-batch is uploaded and computed
+        cum = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        self.src_offsets = cum[:-1].copy() if src_offsets is None else np.ascontiguousarray(src_offsets, dtype=np.int64)
+        if self.src_offsets.shape[0] != U:
+            raise ValueError("src_offsets: one entry per utterance")
+        self.src_extent = int((self.src_offsets + lengths).max()) if U else 0
+        n_dec = np.where(lengths > self.phase, (lengths - self.phase + self.step - 1) // self.step, 0)
+        self.frame_offsets = np.concatenate([[0], np.cumsum(n_dec)]).astype(np.int64)
+        self.total_frames = int(self.frame_offsets[-1])
+        self.total_samples = int(cum[-1])
+        # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that:
+        # nothing can be placed before the first sub-batch is uploaded, filtered and downloaded
+        n_sub = max(1, min(int(n_sub), max(U, 1)))
         per_sub = cum[-1] / n_sub
         marks, size, at = [0.0], per_sub / 8, 0.0
-        while at + size < cum[-1]:
+        while size > 0 and at + size < cum[-1]:
             at += size
             marks.append(at)
             size = min(per_sub, size * 2)
-        cuts = [int(np.searchsorted(cum, m)) for m in marks] + [U]
-        cuts[0] = 0
-        cuts = sorted(set(cuts))
+        cuts = sorted(set([0] + [int(np.searchsorted(cum, m)) for m in marks[1:]] + [U]))
         dev = plan.device
-        self.subs = []
-        row = 0
-        for a, b in zip(cuts[:-1], cuts[1:]):
-            # whole utterances only (target_items=1): same arithmetic as one big batch, bit for bit
-            batch = plan.batch(lengths[a:b], step=step, phase=phase, target_items=1)
-            base = np.concatenate([batch.frame_offsets[u - a] + np.asarray(bases[u], dtype=np.int64)
-                                   for u in range(a, b)] + [np.zeros(0, dtype=np.int64)])
-            # windows that are exactly the label grid (window k = frames k..k+dots-1, k < nb) are written by
-            # the fused kernel itself; anything else goes through the decimated frames and the gather
-            nb = np.maximum(lengths[a:b] // int(step) - self.dots - 1, 0)
-            grid = all(len(bases[u]) == nb[u - a] and
-                       (nb[u - a] == 0 or np.array_equal(np.asarray(bases[u]), np.arange(nb[u - a])))
-                       for u in range(a, b))
-            self.subs.append(dict(batch=batch, base=torch.from_numpy(base).to(dev), s0=int(cum[a]), s1=int(cum[b]),
-                                  r0=row, r1=row + int(base.shape[0]),
-                                  grid=batch.grid_windows(self.dots)[0] if grid else None))
-            row += int(base.shape[0])
-        self.n_windows = row
         C = plan.n_channels
-        max_w = max(s["r1"] - s["r0"] for s in self.subs)
-        max_f = max(s["batch"].total_frames for s in self.subs)
-        self._wave_all = None           # device copy of the whole flat wave buffer (2 B per sample)
-        self._total_s = int(cum[-1])
-        self._win = [torch.empty((max(max_w, 1), self.dots, C), dtype=torch.float32, device=dev) for _ in range(2)]
-        self._dec = torch.empty((max(max_f, 1), C), dtype=torch.float32, device=dev)
-        self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self._ev_in = [torch.cuda.Event() for _ in self.subs]
-        self._ev_done = [torch.cuda.Event() for _ in range(2)]
-        self._ev_free = [torch.cuda.Event() for _ in range(2)]
+        self.subs = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b <= a:
+                continue
+            # whole utterances only (target_items=1): same arithmetic as one big batch, bit for bit
+            batch = plan.batch(lengths[a:b], step=self.step, phase=self.phase, target_items=1)
+            assert batch.total_frames == int(self.frame_offsets[b] - self.frame_offsets[a])
+            # contiguous source spans of this sub-batch (adjacent utterances merge into one copy)
+            so, ln = self.src_offsets[a:b], lengths[a:b]
+            brk = np.flatnonzero(so[1:] != so[:-1] + ln[:-1]) + 1
+            first = np.concatenate([[0], brk])
+            last = np.concatenate([brk, [b - a]])
+            spans = (so[first].copy(), (cum[a:b][first]).copy(), (cum[a:b][last - 1] + ln[last - 1] - cum[a:b][first]).copy())
+            self.subs.append(dict(batch=batch, u0=a, u1=b, s0=int(cum[a]), s1=int(cum[b]), spans=spans,
+                                  f0=int(self.frame_offsets[a]), f1=int(self.frame_offsets[b])))
+        self._wave_dev = None
+        self._stage = None      # pinned staging for pageable input
+        with torch.cuda.device(dev):
+            self._dec_dev = torch.empty((max(self.total_frames, 1), C), dtype=torch.float32, device=dev)
+            self._dec_host = _pinned_empty(max(self.total_frames, 1) * C, torch.float32).view(-1, C)
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._ev_in = [torch.cuda.Event() for _ in self.subs]
+            self._ev_done = [torch.cuda.Event() for _ in self.subs]
+        self.placer = placer if placer is not None else Placer()
 
-    def run(self, wave_host, out_host):
-        """wave_host: flat (pinned) host tensor of all samples; out_host: (N, dots, C) float32
-        host tensor (pinned for full speed).  Returns after everything has landed."""
-        comp = torch.cuda.current_stream()
+    # -- uploads -------------------------------------------------------------------------------
+    def _upload(self, sub, wave_host, esize):
+        src, dst, cnt = sub["spans"]
+        L = _native.lib()
+        check(L.f2_upload_spans(_ptr(self._wave_dev), ctypes.c_void_p(wave_host.data_ptr()),
+                                (src * esize).ctypes.data_as(ctypes.c_void_p), (dst * esize).ctypes.data_as(ctypes.c_void_p),
+                                (cnt * esize).ctypes.data_as(ctypes.c_void_p), int(src.shape[0]),
+                                ctypes.c_void_p(self._s_in.cuda_stream)))
+
+    def _split_runs(self, runs):
+        """runs (global frame numbering) -> one array per sub-batch."""
+        runs = np.ascontiguousarray(runs, dtype=np.int64).reshape(-1, 3)
+        bounds = np.asarray([s["f1"] for s in self.subs], dtype=np.int64)
+        which = np.searchsorted(bounds, runs[:, 0], side="right")
+        if runs.shape[0] and np.all(which[1:] >= which[:-1]):
+            edges = np.searchsorted(which, np.arange(len(self.subs) + 1))
+            return [runs[edges[i]:edges[i + 1]] for i in range(len(self.subs))]
+        order = np.argsort(which, kind="stable")
+        runs, which = runs[order], which[order]
+        edges = np.searchsorted(which, np.arange(len(self.subs) + 1))
+        return [np.ascontiguousarray(runs[edges[i]:edges[i + 1]]) for i in range(len(self.subs))]
+
+    def run(self, wave_host, runs, out_host, keep_frames=False):
+        """wave_host: flat host tensor (int16 / float32 / float64; pinned for full speed -- pageable
+        input is staged through a pinned buffer sub-batch by sub-batch) or a list of per-utterance
+        numpy arrays; runs: (n, 3) int64 from engine.window_runs on this pipeline's frame_offsets;
+        out_host: the (N, dots, C) float32 host array or tensor the rows go to (any host memory).
+        Returns when every row has been placed."""
+        comp = torch.cuda.current_stream(self.plan.device)
         dev = self.plan.device
-        if self._wave_all is None or self._wave_all.dtype != wave_host.dtype:
-            self._wave_all = torch.empty(max(self._total_s, 1), dtype=wave_host.dtype, device=dev)
+        C = self.plan.n_channels
+        listed = isinstance(wave_host, (list, tuple))
+        if listed:
+            dt = torch.from_numpy(wave_host[0][:0]).dtype if len(wave_host) else torch.int16
+            pinned = False
+        else:
+            if not torch.is_tensor(wave_host):
+                wave_host = torch.from_numpy(wave_host)
+            if wave_host.dim() != 1 or wave_host.numel() < self.src_extent:
+                raise ValueError("wave buffer holds %d samples, the pipeline reads up to %d" % (wave_host.numel(), self.src_extent))
+            dt = wave_host.dtype
+            pinned = wave_host.is_pinned()
+        if dt not in _T2F2:
+            raise TypeError("waves must be int16, float32 or float64")
+        if self._wave_dev is None or self._wave_dev.dtype != dt:
+            self._wave_dev = torch.empty(max(self.total_samples, 1), dtype=dt, device=dev)
+        if not pinned and (self._stage is None or self._stage.dtype != dt):
+            self._stage = _pinned_empty(self.total_samples, dt)
+        per_sub = self._split_runs(runs)
+        out_flat = out_host
+        esize = self._wave_dev.element_size()
         self._s_in.wait_stream(comp)
         self._s_out.wait_stream(comp)
-        # all uploads are queued at once (444 MB for the corpus): the H2D traffic is over after the first
-        # few milliseconds and the D2H copies -- the bottleneck -- have the link to themselves afterwards
-        with torch.cuda.stream(self._s_in):
+        if pinned:
+            # all uploads are queued at once (444 MB for the corpus): over after the first few ms
             for i, sub in enumerate(self.subs):
-                self._wave_all[sub["s0"]:sub["s1"]].copy_(wave_host[sub["s0"]:sub["s1"]], non_blocking=True)
+                self._upload(sub, wave_host, esize)
                 self._ev_in[i].record(self._s_in)
         for i, sub in enumerate(self.subs):
-            k = i & 1
+            if not pinned:
+                # pageable input: this sub-batch's samples -> pinned staging -> device, while the
+                # previous sub-batches are being filtered
+                stage = self._stage[sub["s0"]:sub["s1"]].numpy()
+                if listed:
+                    np.concatenate([np.asarray(w).reshape(-1) for w in wave_host[sub["u0"]:sub["u1"]]], out=stage)
+                else:
+                    src, dst, cnt = sub["spans"]
+                    host_np = wave_host.numpy()
+                    for so, do, n in zip(src, dst, cnt):
+                        stage[do - sub["s0"]:do - sub["s0"] + n] = host_np[so:so + n]
+                with torch.cuda.stream(self._s_in):
+                    self._wave_dev[sub["s0"]:sub["s1"]].copy_(self._stage[sub["s0"]:sub["s1"]], non_blocking=True)
+                    self._ev_in[i].record(self._s_in)
             comp.wait_event(self._ev_in[i])
-            if i >= 2:
-                comp.wait_event(self._ev_free[k])  # the D2H of sub-batch i-2 has drained this buffer
-            n_w = sub["r1"] - sub["r0"]
-            if sub["grid"] is not None and n_w:
-                sub["batch"].run(self._wave_all[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff,
-                                 windows=(sub["grid"], self.dots, self._win[k][:n_w]))
-            else:
-                sub["batch"].run(self._wave_all[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff,
-                                 out={"dec": self._dec[:max(sub["batch"].total_frames, 1)]})
-                if n_w:
-                    gather_windows(self._dec, sub["base"], self.dots, 1, out=self._win[k][:n_w])
-            self._ev_done[k].record(comp)
+            dec = self._dec_dev[sub["f0"]:sub["f1"]]
+            sub["batch"].run(self._wave_dev[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff, out={"dec": dec},
+                             stream=comp)
+            self._ev_done[i].record(comp)
             with torch.cuda.stream(self._s_out):
-                self._s_out.wait_event(self._ev_done[k])
-                if n_w:
-                    out_host[sub["r0"]:sub["r1"]].copy_(self._win[k][:n_w], non_blocking=True)
-                self._ev_free[k].record(self._s_out)
+                self._s_out.wait_event(self._ev_done[i])
+                if sub["f1"] > sub["f0"]:
+                    self._dec_host[sub["f0"]:sub["f1"]].copy_(dec, non_blocking=True)
+                if per_sub[i].shape[0]:
+                    self.placer.submit(self._dec_host, per_sub[i], out_flat, dots=self.dots, stream=self._s_out)
         comp.wait_stream(self._s_out)
+        self._s_out.synchronize()
+        self.placer.wait()
         return out_host
+
+    @property
+    def frames_host(self):
+        """The decimated frames of the last run ([total_frames, C] float32, pinned host memory)."""
+        return self._dec_host[:self.total_frames]
 
 
 class MultiGpuWindowPipeline:
-    """WindowPipeline over several GPUs of one box from ONE process: the utterances are cut into
-    contiguous ranges of about equal sample count, one per device; every device runs its own
-    WindowPipeline into its slice of the shared host output.  Utterances are independent, so
-    there is no collective -- the "gather" is each device's D2H copy landing at its row offset
-    (SURVEY.md section 8e).  All launches are asynchronous; one host thread drives all devices."""
+    """WindowPipeline over several GPUs of one box from ONE process: the utterances are dealt to
+    the devices by shard_utterances (length-sorted round-robin), every device runs its own
+    WindowPipeline over its shard, reading its utterances out of the one host wave buffer and
+    placing its rows at their final offsets in the one host output.  Utterances are independent,
+    so there is no collective -- the "gather" is each device's frames landing on the host and
+    being placed.  One host thread drives all devices; the placement pool is
+    shared."""
 
-    def __init__(self, coefs, lengths, bases, devices=None, **kw):
-        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    def __init__(self, coefs, lengths, devices=None, **kw):
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(-1)
         if devices is None:
             devices = list(range(torch.cuda.device_count()))
-        U = int(lengths.shape[0])
-        devices = list(devices)[:max(1, min(len(devices), U))]
-        cum = np.concatenate([[0], np.cumsum(lengths)])
-        cuts = [int(np.searchsorted(cum, cum[-1] * k / len(devices))) for k in range(len(devices) + 1)]
-        cuts[0], cuts[-1] = 0, U
+        devices = list(devices)[:max(1, min(len(devices), max(len(lengths), 1)))]
+        self.lengths = lengths
+        cum = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        self.placer = kw.pop("placer", None) or Placer()
         self.parts = []
-        row = 0
-        for d, a, b in zip(devices, cuts[:-1], cuts[1:]):
-            if b <= a:
-                continue
+        for d, idx in zip(devices, shard_utterances(lengths, len(devices))):
             with torch.cuda.device(d):
-                plan = plan_for(coefs, d)
-                pipe = WindowPipeline(plan, lengths[a:b], bases[a:b], **kw)
-            self.parts.append(dict(device=d, pipe=pipe, s0=int(cum[a]), s1=int(cum[b]), r0=row, r1=row + pipe.n_windows))
-            row += pipe.n_windows
-        self.n_windows = row
+                pipe = WindowPipeline(plan_for(coefs, d), lengths[idx], src_offsets=cum[idx], placer=self.placer, **kw)
+            self.parts.append(dict(device=d, utts=idx, pipe=pipe))
 
-    def run(self, wave_host, out_host):
+    def window_runs(self, centers, counts, radius=5):
+        """Per-device runs for centres given in corpus order (rows in corpus order)."""
+        counts = np.asarray(counts, dtype=np.int64)
+        centers = np.asarray(centers, dtype=np.int64)
+        cpos = np.concatenate([[0], np.cumsum(counts)])
+        out = []
         for part in self.parts:
+            idx, pipe = part["utts"], part["pipe"]
+            cen = np.concatenate([centers[cpos[u]:cpos[u + 1]] for u in idx] + [np.zeros(0, np.int64)])
+            runs, phase, _ = window_runs(cen, counts[idx], self.lengths[idx], pipe.frame_offsets, radius, pipe.step,
+                                         pipe.phase, row_offsets=cpos[idx])
+            if runs is None or phase != pipe.phase:
+                raise ValueError("timepoints are not windows of consecutive frames of the pipeline's grid")
+            out.append(runs)
+        return out
+
+    def run(self, wave_host, runs_per_part, out_host):
+        import concurrent.futures as cf
+        # every device needs its own driving thread only for the final wait; launches are asynchronous
+        def drive(part, runs):
             with torch.cuda.device(part["device"]):
-                part["pipe"].run(wave_host[part["s0"]:part["s1"]], out_host[part["r0"]:part["r1"]])
-        for part in self.parts:
-            torch.cuda.synchronize(part["device"])
+                part["pipe"].run(wave_host, runs, out_host)
+        with cf.ThreadPoolExecutor(max_workers=len(self.parts)) as pool:
+            list(pool.map(drive, self.parts, runs_per_part))
         return out_host
 
 
@@ -421,7 +563,7 @@ _plans_lock = threading.Lock()
 
 
 def plan_for(coefs, device=None):
-    """Plans are immutable; cache them by the bytes of the coefficient matrix."""
+    """One shared, immutable plan per (coefficient matrix, device)."""
     _require_cuda()
     coefs = np.ascontiguousarray(coefs, dtype=np.float64)
     dev = torch.cuda.current_device() if device is None else int(device)
@@ -430,6 +572,7 @@ def plan_for(coefs, device=None):
         p = _plans.get(key)
         if p is None:
             p = Plan(coefs, dev)
+            p._frozen = True
             _plans[key] = p
         return p
 
@@ -446,3 +589,137 @@ def any_plan(device=None):
                 return p
     from .gammatone import filters
     return plan_for(filters.make_erb_filters(16000, filters.centre_freqs(16000, 4, 100)), dev)
+
+
+# ---- host side of the window stage (f2_host.cpp; HOST memory, no device needed) ----------------
+def window_runs(centers, counts, lengths, frame_offsets, radius=5, step=160, phase=-1, row_offsets=None):
+    """Label timepoints -> runs of consecutive windows on the decimated grid (f2_window_runs).
+
+    centers: int64 window centres of all utterances back to back; counts[u] of them belong to
+    utterance u (InputGenerator.py:73-80 output order).  Returns (runs, phase, n_rows): runs is an
+    (n, 3) int64 array of (first_frame, row0, count), or None when the timepoints are legal but not
+    windows of consecutive frames of one grid.  Raises IndexError where the reference would."""
+    centers = np.ascontiguousarray(centers, dtype=np.int64).reshape(-1)
+    counts = np.ascontiguousarray(counts, dtype=np.int64).reshape(-1)
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(-1)
+    frame_offsets = np.ascontiguousarray(frame_offsets, dtype=np.int64).reshape(-1)
+    n_utts = int(counts.shape[0])
+    if lengths.shape[0] != n_utts or frame_offsets.shape[0] < n_utts or int(counts.sum()) != centers.shape[0]:
+        raise ValueError("window_runs: counts / lengths / frame_offsets / centers do not fit together")
+    rows = None
+    if row_offsets is not None:
+        rows = np.ascontiguousarray(row_offsets, dtype=np.int64).reshape(-1)
+        if rows.shape[0] < n_utts:
+            raise ValueError("window_runs: row_offsets shorter than the utterance list")
+    L = _native.lib()
+    ph = ctypes.c_int(int(phase))
+    n_runs, n_rows = ctypes.c_int64(), ctypes.c_int64()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None and a.size else None
+
+    def call(buf, room):
+        ph.value = int(phase)
+        rc = L.f2_window_runs(p(centers), p(counts), p(lengths), p(frame_offsets), p(rows), n_utts, int(radius),
+                              int(step), ctypes.byref(ph), p(buf), room, ctypes.byref(n_runs), ctypes.byref(n_rows))
+        if rc == _native.F2_ERR_INDEX:
+            raise IndexError(L.f2_last_error().decode("utf-8", "replace"))
+        check(rc)
+
+    call(None, 0)  # count
+    if n_runs.value < 0:
+        return None, ph.value, n_rows.value
+    runs = np.empty((max(n_runs.value, 1), 3), dtype=np.int64)
+    call(runs, n_runs.value)
+    return runs[:n_runs.value], ph.value, n_rows.value
+
+
+def _host_ptr(a):
+    if torch.is_tensor(a):
+        if a.device.type != "cpu" or not a.is_contiguous():
+            raise ValueError("host placement wants contiguous CPU tensors")
+        return ctypes.c_void_p(a.data_ptr())
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("host placement wants C-contiguous arrays")
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check_placement(frames, runs, out, dots):
+    C = int(frames.shape[-1])
+    if str(frames.dtype).split(".")[-1] != "float32" or str(out.dtype).split(".")[-1] != "float32":
+        raise TypeError("host placement copies float32 frames into float32 rows")
+    runs = np.ascontiguousarray(runs, dtype=np.int64).reshape(-1, 3)
+    if runs.shape[0]:
+        n_frames = int(np.prod(frames.shape[:-1]))
+        n_rows = int(np.prod(out.shape)) // (int(dots) * C)
+        live = runs[runs[:, 2] > 0]
+        if live.shape[0] and (live.min() < 0 or int((live[:, 0] + live[:, 2]).max()) + int(dots) - 1 > n_frames or
+                              int((live[:, 1] + live[:, 2]).max()) > n_rows):
+            raise IndexError("a window run leaves the frame matrix or the output tensor")
+    return runs, C
+
+
+def place_windows(frames, runs, out, dots=11, threads=0):
+    """out[row0+i, j, :] = frames[first_frame+i+j, :] for every run (f2_place_windows): the rows of
+    InputGenerator.py:73-80 from decimated frames, one contiguous copy per row.  Host arrays."""
+    runs, C = _check_placement(frames, runs, out, dots)
+    check(_native.lib().f2_place_windows(_host_ptr(frames), C, int(dots), runs.ctypes.data_as(ctypes.c_void_p),
+                                         int(runs.shape[0]), _host_ptr(out), int(threads)))
+    return out
+
+
+class Placer:
+    """Persistent host worker pool that places window rows in CUDA stream order (f2_placer_*)."""
+
+    def __init__(self, threads=0):
+        self._h = ctypes.c_void_p()
+        check(_native.lib().f2_placer_create(int(threads), ctypes.byref(self._h)))
+        self.threads = int(_native.lib().f2_placer_threads(self._h))
+        self._keep = []
+
+    def submit(self, frames, runs, out, dots=11, stream=None, after_stream=True):
+        """Queue a placement; with after_stream it starts once everything queued on `stream` (default:
+        the current stream) so far -- the D2H copy of `frames` -- has completed."""
+        runs, C = _check_placement(frames, runs, out, dots)
+        self._keep.append((frames, out))  # keep the buffers alive until wait()
+        sp = _stream_ptr(stream) if after_stream else ctypes.c_void_p(0)
+        check(_native.lib().f2_placer_submit(self._h, int(bool(after_stream)), sp, _host_ptr(frames), C, int(dots),
+                                             runs.ctypes.data_as(ctypes.c_void_p), int(runs.shape[0]), _host_ptr(out)))
+
+    def wait(self):
+        check(_native.lib().f2_placer_wait(self._h))
+        self._keep.clear()
+
+    def __del__(self):
+        try:
+            h = getattr(self, "_h", None)
+            if h is not None and h.value:
+                _native.lib().f2_placer_destroy(h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class _HostBlock:
+    def __init__(self, nbytes):
+        self.nbytes = max(int(nbytes), 1)
+        self.ptr = ctypes.c_void_p()
+        check(_native.lib().f2_host_alloc(self.nbytes, ctypes.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            if self.ptr is not None and self.ptr.value:
+                _native.lib().f2_host_free(self.ptr, self.nbytes)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def host_empty(shape, dtype=np.float32):
+    """Uninitialised numpy array on huge-page advised anonymous memory (f2_host_alloc): the fresh
+    output tensor of a corpus-sized request without two million 4 KiB page faults."""
+    shape = tuple(int(s) for s in shape)
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    block = _HostBlock(nbytes)
+    buf = (ctypes.c_char * block.nbytes).from_address(block.ptr.value)
+    buf._f2_block = block  # the mapping lives as long as the ctypes view numpy holds on to
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)

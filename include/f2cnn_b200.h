@@ -37,7 +37,8 @@ extern "C" {
 #define F2_ERR_INVALID 1     /* bad argument */
 #define F2_ERR_CUDA 2        /* CUDA runtime error (see f2_last_error) */
 #define F2_ERR_WORKSPACE 3   /* workspace too small */
-#define F2_ERR_UNSUPPORTED 4 /* size outside the supported range */
+#define F2_ERR_UNSUPPORTED 4 /* size or filterbank outside the supported range */
+#define F2_ERR_INDEX 5       /* a window index leaves its utterance (the reference raises IndexError) */
 
 /* sample / matrix element types */
 #define F2_I16 0
@@ -84,6 +85,9 @@ F2_API int f2_batch_frame_offsets(const f2_batch* batch, int64_t* frame_offsets)
 F2_API size_t f2_batch_workspace_bytes(const f2_batch* batch, int want_full_gfb, int want_full_env);
 
 typedef struct f2_run_args {
+    uint32_t struct_size; /* = sizeof(f2_run_args) of the caller's header: a struct that is shorter than
+                           * the library's (an older binding) is rejected with F2_ERR_INVALID instead
+                           * of being read past its end */
     const void* wave; /* flat samples of all utterances, wave_dtype                        */
     int wave_dtype;   /* F2_I16 (WAV), F2_F32, F2_F64 (noise-mixed, Evaluating.py:200)     */
     int lpf;          /* LPF flag of ExtractEnvelopeFromMatrix (EnvelopeExtraction.py:51)  */
@@ -100,8 +104,9 @@ typedef struct f2_run_args {
      * builds for a label CSV whose timepoints are consecutive grid steps, InputGenerator.py:73-83 with
      * LabelDataGenerator.py:48-50): window k of utterance u = decimated frames k .. k+win_dots-1, for
      * k < win_offsets[u+1] - win_offsets[u]; it is row win_offsets[u] + k of `windows`
-     * ([rows][win_dots][C] float32).  win_offsets: DEVICE array of n_utts+1 row offsets.  Arbitrary
-     * timepoints take `dec` + f2_gather_windows instead. */
+     * ([rows][win_dots][C] float32, rows >= win_offsets[n_utts]: the caller sizes it from its host copy
+     * of the offsets).  win_offsets: DEVICE array of n_utts+1 row offsets.  Arbitrary timepoints take
+     * `dec` + f2_gather_windows (or f2_place_windows on the host) instead. */
     float* windows;             /* out, nullable */
     const int64_t* win_offsets; /* device, required with windows */
     int win_dots;               /* 2*RADIUS+1 */
@@ -148,6 +153,52 @@ F2_API int f2_gather_windows_cn(const void* env, int dtype, int n_channels, int6
 F2_API int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int64_t i0, int64_t i1, int normalize,
                     void* out, int out_dtype, int* bad_flag, void* stream);
 
+/* ---- host side of the window stage ---------------------------------------------------------
+ * All pointers in this section are HOST pointers and none of these functions needs a device.
+ * When every timepoint of the label CSV lies on the decimated grid, row k of the reference's input
+ * tensor (InputGenerator.py:73-80) is the block of `dots` CONSECUTIVE decimated frames that starts
+ * at frame (center - RADIUS*STEP - phase)/STEP: the (N, dots, C) tensor repeats every frame `dots`
+ * times.  Instead of copying that tensor over PCIe, the frames (`dec` of f2_batch_run) can travel
+ * and the rows be placed on the host: one contiguous copy of dots*C floats per row, bit patterns
+ * untouched. */
+typedef struct f2_win_run {
+    int64_t first_frame; /* row of the [frame][C] matrix where the first window of the run starts */
+    int64_t row0;        /* output row of that window                                            */
+    int64_t count;       /* windows in the run: window i = frames first_frame+i .. +dots-1 -> row0+i */
+} f2_win_run;
+
+/* Label timepoints -> runs.  centers: the window centres of all utterances back to back (counts[u] of
+ * them for utterance u, in output order); lengths[u]: samples; frame_offsets: as returned by
+ * f2_batch_frame_offsets for a batch with the same step and *phase; row_offsets: first output row of
+ * each utterance, or NULL for rows in utterance order.  *phase < 0 on entry: taken from the first
+ * window ((center - radius*step) mod step) and returned.  Index semantics of InputGenerator.py:76: an
+ * index in [-n, 0) wraps like a Python index, any other index outside [0, n) fails with
+ * F2_ERR_INDEX.  *n_runs = -1 when the timepoints are legal but are not all windows of consecutive
+ * frames of ONE grid (a wrapping window, mixed phases): such requests take f2_gather_index instead.
+ * runs == NULL only counts. */
+F2_API int f2_window_runs(const int64_t* centers, const int64_t* counts, const int64_t* lengths,
+                          const int64_t* frame_offsets, const int64_t* row_offsets, int n_utts, int radius, int step,
+                          int* phase, f2_win_run* runs, int64_t max_runs, int64_t* n_runs, int64_t* n_rows);
+/* out[(row0+i)][j][c] = frames[first_frame+i+j][c] for every run, on n_threads host threads (<= 0:
+ * all the calling thread may run on), non-temporal stores.  Synchronous. */
+F2_API int f2_place_windows(const float* frames, int n_channels, int dots, const f2_win_run* runs, int64_t n_runs,
+                            float* out, int n_threads);
+/* The same on a persistent worker pool fed in stream order: with after_stream != 0 the job becomes
+ * runnable when everything queued on `stream` before this call has completed (cudaLaunchHostFunc) --
+ * e.g. the device->host copy of `frames` -- so the host never blocks between sub-batches.  `runs` is
+ * copied; frames and out must stay valid until f2_placer_wait returns. */
+typedef struct f2_placer f2_placer;
+F2_API int f2_placer_create(int n_threads, f2_placer** out);
+F2_API int f2_placer_destroy(f2_placer* placer);
+F2_API int f2_placer_threads(const f2_placer* placer);
+F2_API int f2_placer_submit(f2_placer* placer, int after_stream, void* stream, const float* frames, int n_channels,
+                            int dots, const f2_win_run* runs, int64_t n_runs, float* out);
+F2_API int f2_placer_wait(f2_placer* placer);
+/* Anonymous host memory advised to use transparent huge pages (a fresh 7.5 GB tensor of 4 KiB pages
+ * costs two million page faults on its first write). */
+F2_API int f2_host_alloc(size_t bytes, void** out);
+F2_API int f2_host_free(void* ptr, size_t bytes);
+
 /* ---- label generation ---------------------------------------
  * Least-squares line through the `dots` = 2*RADIUS+1 formant frames around each timepoint and the
  * two-sided p-value of its Pearson correlation: the body of the step loop of
@@ -159,6 +210,12 @@ F2_API int f2_dense_frames(const float* env_t, int n_channels, int dots, int ste
  * arithmetic throughout (the CSV keeps round(a, 5), round(p, 5)). */
 F2_API int f2_label_fit(const double* formant, const int64_t* first, const int32_t* center, int64_t n_items, int dots,
                         int step, double* out, void* stream);
+
+/* Host -> device upload of n_spans byte ranges on `stream` (cudaMemcpyAsync each): the utterances of a
+ * shard picked out of one host buffer that holds the whole corpus.  src_host should be page-locked
+ * for the copies to be asynchronous.  Offsets and sizes in bytes, HOST arrays. */
+F2_API int f2_upload_spans(void* dst_device, const void* src_host, const int64_t* src_off, const int64_t* dst_off,
+                           const int64_t* nbytes, int64_t n_spans, void* stream);
 
 /* ---- CUDA event helpers so that a host without a CUDA binding can time on the device ----- */
 F2_API int f2_event_create(void** event);

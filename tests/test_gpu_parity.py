@@ -355,31 +355,6 @@ def test_other_filterbanks_and_dtypes(gpu, oracle, fs, C, low, n, dtype):
         assert np.array_equal(res["dec"].cpu().numpy(), env[:, ::160].astype(np.float32).T)
 
 
-def test_experimental_lane_stream_kernel(gpu, oracle, monkeypatch):
-    """f2_lanes.cu (opt-in, F2_USE_LANES=1): lane = stream, warp = channel, uniform-register
-    coefficients.  Same decimated frames as the default kernel to float32 noise, and parity."""
-    api, engine, filters, torch = gpu
-    from f2cnn_b200 import synth
-    co = coefs128()
-    lens = [20000, 33000, 4100, 64]
-    waves = [synth.white_noise_i16(n, seed=70 + i) for i, n in enumerate(lens)]
-    flat = torch.from_numpy(np.concatenate(waves)).cuda()
-    plan = engine.plan_for(co)
-    for target in (1, 0):
-        batch = plan.batch(lens, target_items=target)
-        ref = batch.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
-        monkeypatch.setenv("F2_USE_LANES", "1")
-        got = batch.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
-        monkeypatch.delenv("F2_USE_LANES")
-        for u, (n, w) in enumerate(zip(lens, waves)):
-            _, eo, _ = oracle.utterance(w, co, True, 50)
-            scale = np.maximum(np.sqrt(np.mean(eo ** 2, axis=1)), 1e-3 * np.abs(eo).max())[None, :]
-            f0, f1 = batch.frame_offsets[u], batch.frame_offsets[u + 1]
-            tol = TOL if n >= 255 else 2e-3
-            assert np.max(np.abs(got[f0:f1] - eo[:, ::160].T) / scale) <= tol, (target, u)
-            assert np.max(np.abs(got[f0:f1] - ref[f0:f1]) / scale) <= max(5e-5, tol / 2), (target, u)
-
-
 def test_corpus_sized_request_takes_the_pipelined_path(gpu, monkeypatch):
     """features_to_windows on many utterances: the sub-batched, three-stream pipeline returns
     exactly what the single-launch path returns."""

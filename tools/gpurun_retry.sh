@@ -1,0 +1,9 @@
+#!/bin/bash
+# gpurun with retries while the pod answers "busy" (exit code 3): tools/gpurun_retry.sh <timeout> '<command>'
+for i in $(seq 1 30); do
+  /usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$1" -- "$2"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3

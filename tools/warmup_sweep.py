@@ -8,7 +8,7 @@ from f2cnn_b200.gammatone import filters
 from oracle import oracle
 
 co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, 100))
-plan = engine.plan_for(co)
+plan = engine.Plan(co)  # private plan: set_warmup is refused on the cached ones
 print("defaults", plan.get_warmup())
 cases = {"white": synth.white_noise_i16(48000, seed=0), "speech": synth.speech_like_i16(40000, seed=1)}
 ref = {k: oracle.utterance(w, co, True, 50)[1] for k, w in cases.items()}
