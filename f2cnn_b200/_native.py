@@ -61,6 +61,8 @@ SIGNATURES = {
     "f2_abi_version": (ctypes.c_int, []),
     "f2_plan_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_void_p)]),
+    "f2_bank_check": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_int)]),
     "f2_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "f2_plan_channels": (ctypes.c_int, [ctypes.c_void_p]),
     "f2_plan_set_warmup": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),

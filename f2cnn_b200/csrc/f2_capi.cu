@@ -79,6 +79,125 @@ void butter1(double cutoff_hz, double* b0, double* a1) {
     *a1 = -(4.0 - w) / (4.0 + w);
 }
 
+// ---- float32 tolerance guard -------------------------------------------------------------------
+// The kernels compute in float32 and are held to 1e-4 x channel RMS against the reference's float64
+// (north star).  How close a bank's poles may come to z = 1 before float32 round-off breaks that
+// depends on more than 1 + B1 + B2 (LOW_FREQ = 20 Hz passes at width 1 and 0.5 and fails at width 2
+// under a loud tone in the stop band, profiles/r01o_fuzz.log), so instead of a formula the plan is
+// TRIED: the real cascade of the channels nearest to z = 1 is run here on the host, once in float32
+// with exactly the kernel's operations (fmaf = FFMA, same order, same dithered coefficients, same
+// section form per channel group) and once in float64, on probe signals that cover the observed worst
+// cases -- loud tones far above the channel and white noise.  The error is measured the way the
+// parity tests measure it: max |y32 - y64| over max(channel RMS, 1 % of the loudest channel's).
+struct ProbeChan {
+    float z[4], cq[4], ncy[4], nb1[4], g4;
+    double zd[4], b1, b2, g4d;
+    bool direct;
+};
+
+double probe_channel(const ProbeChan& p, const float* x, int n, double loudest_rms) {
+    float y[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, up0 = 0.f;
+    double Y[4] = {0, 0, 0, 0}, Y2[4] = {0, 0, 0, 0}, UP0 = 0.0;
+    double err = 0.0, power = 0.0;
+    for (int t = 0; t < n; ++t) {
+        // float32, as cascade_real<FORM> of f2_fused.cu
+        float u = x[t], up = up0;
+        up0 = u;
+        for (int i = 0; i < 4; ++i) {
+            const float in = fmaf(p.z[i], up, u);
+            const float yo = y[i];
+            float yn;
+            if (!p.direct) {
+                float qn = fmaf(p.cq[i], q[i], in);
+                qn = fmaf(p.ncy[i], yo, qn);
+                yn = yo + qn;
+                q[i] = qn;
+            } else {
+                yn = fmaf(p.nb1[i], yo, fmaf(-p.cq[i], q[i], in));
+                q[i] = yo;
+            }
+            y[i] = yn;
+            up = yo;
+            u = yn;
+        }
+        // float64, exact coefficients: y[t] = in - b1 y[t-1] - b2 y[t-2]
+        double U = x[t], UP = UP0;
+        UP0 = U;
+        for (int i = 0; i < 4; ++i) {
+            const double in = U + p.zd[i] * UP;
+            const double yo = Y[i];
+            const double yn = in - p.b1 * yo - p.b2 * Y2[i];
+            Y2[i] = yo;
+            Y[i] = yn;
+            UP = yo;
+            U = yn;
+        }
+        const double ref = Y[3] * p.g4d;
+        err = std::max(err, fabs((double)(p.g4 * y[3]) - ref));
+        power += ref * ref;
+    }
+    const double scale = std::max(sqrt(power / n), 0.01 * loudest_rms);
+    return scale > 0.0 ? err / scale : 0.0;
+}
+
+// worst predicted error of the bank, in units of the 1e-4 tolerance
+double bank_float32_error(const double* coefs, int C, int* worst_channel) {
+    constexpr int kProbeLen = 8192, kChannels = 6;
+    constexpr double kAmp = 8000.0;
+    // the channels nearest to z = 1
+    std::vector<int> order((size_t)C);
+    for (int c = 0; c < C; ++c) order[(size_t)c] = c;
+    auto cy_of = [&](int c) { return 1.0 + (coefs[(size_t)c * 10 + 7] + coefs[(size_t)c * 10 + 8]) / coefs[(size_t)c * 10 + 6]; };
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return cy_of(a) < cy_of(b); });
+    order.resize((size_t)std::min(C, kChannels));
+    std::vector<float> x((size_t)kProbeLen);
+    double worst = 0.0;
+    if (worst_channel) *worst_channel = order.empty() ? 0 : order[0];
+    const double tones[] = {M_PI / 2.0, M_PI / 8.0, 0.1727875959474386 /* 440 Hz at 16 kHz */, 0.0 /* white noise */};
+    for (double w : tones) {
+        double loudest;
+        if (w > 0.0) {
+            for (int t = 0; t < kProbeLen; ++t) x[(size_t)t] = (float)rint(kAmp * sin(w * t));
+            loudest = kAmp / M_SQRT2;  // the channel centred on the tone passes it with unit gain
+        } else {
+            uint64_t st = 0x9E3779B97F4A7C15ull;
+            for (int t = 0; t < kProbeLen; ++t) {  // sum of 4 uniforms: near-Gaussian, sigma ~ 3000 like the bench input
+                double acc = 0.0;
+                for (int k = 0; k < 4; ++k) {
+                    st = st * 6364136223846793005ull + 1442695040888963407ull;
+                    acc += (double)(st >> 40) / (double)(1 << 24) - 0.5;
+                }
+                x[(size_t)t] = (float)rint(acc * 3000.0 * sqrt(3.0));
+            }
+            loudest = 0.0;  // broadband: every channel is held to its own RMS
+        }
+        for (int c : order) {
+            const double* k = coefs + (size_t)c * 10;
+            ProbeChan p;
+            const double b1 = k[7] / k[6], b2 = k[8] / k[6], a0n = k[0] / k[6];
+            dither4(b2, p.cq);
+            dither4(-(1.0 + b1 + b2), p.ncy);
+            dither4(-b1, p.nb1);
+            for (int s = 0; s < 4; ++s) {
+                p.zd[s] = k[1 + s] / k[0];
+                p.z[s] = (float)p.zd[s];
+            }
+            p.b1 = b1, p.b2 = b2;
+            p.g4d = a0n * a0n * a0n * a0n / k[9];
+            p.g4 = (float)p.g4d;
+            double group_cy = 1e300;  // the kernel picks the section form per group of 32 channels
+            for (int cc = c / 32 * 32; cc < std::min(C, c / 32 * 32 + 32); ++cc) group_cy = std::min(group_cy, cy_of(cc));
+            p.direct = group_cy >= kDirectMinCyGfb;
+            const double e = probe_channel(p, x.data(), kProbeLen, loudest) / 1e-4;
+            if (e > worst) {
+                worst = e;
+                if (worst_channel) *worst_channel = c;
+            }
+        }
+    }
+    return worst;
+}
+
 }  // namespace
 
 // error channel of the other translation units of the library (f2_host.cpp); not exported
@@ -133,6 +252,17 @@ int f2_lowpass_coefficients(double cutoff_hz, double* b0, double* a1) {
     return F2_OK;
 }
 
+int f2_bank_check(const double* coefs, int n_channels, double* predicted, int* worst_channel) {
+    if (!coefs || n_channels <= 0 || !predicted) return fail(F2_ERR_INVALID, "f2_bank_check: bad arguments");
+    for (int c = 0; c < n_channels; ++c) {
+        const double* k = coefs + (size_t)c * 10;
+        if (!(k[6] != 0.0) || !(k[0] != 0.0) || !(k[9] > 0.0) || !isfinite(k[9]))
+            return fail(F2_ERR_INVALID, "channel %d: A0 == 0, B0 == 0 or gain <= 0", c);
+    }
+    *predicted = bank_float32_error(coefs, n_channels, worst_channel);
+    return F2_OK;
+}
+
 int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** out) {
     if (!coefs || !out || n_channels <= 0) return fail(F2_ERR_INVALID, "f2_plan_create: bad arguments");
     int ndev = 0;
@@ -184,6 +314,17 @@ int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** ou
             cy = std::min(cy, 1.0 + (k[7] + k[8]) / k[6]);
         }
         for (int c = g0; c < g0 + 32; ++c) par[(size_t)f2::P_FORM * c_pad + c] = (float)cy;
+    }
+    {
+        // a bank whose float32 result would leave the stated tolerance is refused, not answered quietly
+        int bad = 0;
+        const double predicted = bank_float32_error(coefs, C, &bad);
+        if (predicted > 1.0 && !getenv("F2CNN_B200_ALLOW_IMPRECISE"))
+            return fail(F2_ERR_UNSUPPORTED,
+                        "filterbank too close to z = 1 for float32: channel %d (1+B1+B2 = %.3g) is predicted to miss "
+                        "the 1e-4 x RMS tolerance by %.1fx (f2_bank_check); widen LOW_FREQ / lower `width`, or set "
+                        "F2CNN_B200_ALLOW_IMPRECISE=1 to run anyway", bad,
+                        1.0 + (coefs[(size_t)bad * 10 + 7] + coefs[(size_t)bad * 10 + 8]) / coefs[(size_t)bad * 10 + 6], predicted);
     }
     f2_plan* p = new (std::nothrow) f2_plan();
     if (!p) return fail(F2_ERR_INVALID, "out of host memory");

@@ -44,7 +44,7 @@ struct UttDesc {
     int log2N2;
 };
 
-// One CTA's work: channels [cblock*128, +128) of utterance `utt`, output samples [t0, t1).
+// One CTA (= one warp) of work: channels [cblock*32, +32) of utterance `utt`, output samples [t0, t1).
 struct Item {
     int utt;
     int cblock;

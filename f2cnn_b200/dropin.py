@@ -32,12 +32,16 @@ _MODULES = {
 
 # names that reference modules bind with `from X import name`
 _REBIND = {
+    # scripts/plotting/PlottingProcessing.py:12-15
     "scripts.plotting.PlottingProcessing": {
+        "centre_freqs": ("gammatone.filters", "centre_freqs"),
+        "make_erb_filters": ("gammatone.filters", "make_erb_filters"),
         "ExtractEnvelopeFromMatrix": ("scripts.processing.EnvelopeExtraction", "ExtractEnvelopeFromMatrix"),
+        "ExtractFBFile": ("scripts.processing.FBFileReader", "ExtractFBFile"),
+        "GetFilteredOutputFromFile": ("scripts.processing.GammatoneFiltering", "GetFilteredOutputFromFile"),
         "GetArrayFromWAV": ("scripts.processing.GammatoneFiltering", "GetArrayFromWAV"),
-        "GetFilteredOutputFromArray": ("scripts.processing.GammatoneFiltering", "GetFilteredOutputFromArray"),
-        "filters": ("gammatone", "filters"),
     },
+    # f2cnn.py:4-9
     "f2cnn": {
         "FilterAllOrganisedFiles": ("scripts.processing.GammatoneFiltering", "FilterAllOrganisedFiles"),
         "ExtractAllEnvelopes": ("scripts.processing.EnvelopeExtraction", "ExtractAllEnvelopes"),

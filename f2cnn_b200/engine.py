@@ -39,6 +39,18 @@ def lowpass_coefficients(cutoff_hz):
     return b0.value, a1.value
 
 
+def bank_check(coefs):
+    """(predicted worst float32 error in units of the 1e-4 x RMS tolerance, channel) of a
+    make_erb_filters bank -- the host-only check Plan() applies (f2_bank_check)."""
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    if coefs.ndim != 2 or coefs.shape[1] != 10:
+        raise ValueError("coefs must be (n_channels, 10) as returned by make_erb_filters")
+    pred, chan = ctypes.c_double(), ctypes.c_int()
+    check(_native.lib().f2_bank_check(coefs.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(coefs.shape[0]),
+                                      ctypes.byref(pred), ctypes.byref(chan)))
+    return pred.value, chan.value
+
+
 class Plan:
     """One gammatone filterbank on one device.  coefs = make_erb_filters output (C,10)."""
 
@@ -359,7 +371,7 @@ class WindowPipeline:
     holds the whole corpus.  Frames are numbered over the pipeline's utterances in order
     (`frame_offsets`), which is what engine.window_runs wants."""
 
-    def __init__(self, plan, lengths, dots=11, step=160, phase=0, lpf=True, cutoff=50, n_sub=16, src_offsets=None,
+    def __init__(self, plan, lengths, dots=11, step=160, phase=0, lpf=True, cutoff=50, n_sub=None, src_offsets=None,
                  placer=None):
         self.plan, self.dots, self.lpf, self.cutoff = plan, int(dots), bool(lpf), cutoff
         self.step, self.phase = int(step), int(phase)
@@ -377,7 +389,10 @@ class WindowPipeline:
         self.total_samples = int(cum[-1])
         # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that:
         # nothing can be placed before the first sub-batch is uploaded, filtered and downloaded
-        n_sub = max(1, min(int(n_sub), max(U, 1)))
+        if n_sub is None:
+            # a sub-batch should still fill the device: 592 utterances x 4 channel groups = one wave of CTAs
+            n_sub = U // 512
+        n_sub = max(1, min(int(n_sub), 16, max(U, 1)))
         per_sub = cum[-1] / n_sub
         marks, size, at = [0.0], per_sub / 8, 0.0
         while size > 0 and at + size < cum[-1]:

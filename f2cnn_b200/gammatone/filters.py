@@ -2,7 +2,7 @@
 
 Coefficient design (erb_point / erb_space / centre_freqs / make_erb_filters) stays on the
 host in float64 -- it is 0.2 ms of work whose output is the kernels' parameter block, and
-it reproduces the reference bit for bit (tests/test_filters_host.py compares with `==`
+it reproduces the reference bit for bit (tests/test_host_cpu.py::test_filters_bit_exact_vs_reference_golden compares with `==`
 against tests/golden/coefs.npz).  erb_filterbank runs on the B200 through
 libf2cnn_b200.so; there is no CPU implementation of it in this package.
 

@@ -58,6 +58,14 @@ F2_API int f2_abi_version(void);
  * A0, A11, A12, A13, A14, A2, B0, B1, B2, gain).  Derives the float32 per-channel
  * parameter block in float64 and uploads it to `device`. */
 F2_API int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** out);
+/* Host-only check f2_plan_create applies (no device needed).  The kernels compute in float32 and are
+ * held to 1e-4 x channel RMS against the reference's float64: the real cascade of the channels
+ * nearest to z = 1 is run on the host in float32 with the kernel's exact operations and in float64,
+ * on probe signals (loud tones, white noise); *predicted = worst error in units of that tolerance,
+ * *worst_channel (nullable) where.  f2_plan_create fails with F2_ERR_UNSUPPORTED when it exceeds 1
+ * (make_erb_filters(fs, cf, width) is public API, gammatone/filters.py:89: e.g. LOW_FREQ = 20 Hz with
+ * width = 2), unless the environment sets F2CNN_B200_ALLOW_IMPRECISE. */
+F2_API int f2_bank_check(const double* coefs, int n_channels, double* predicted, int* worst_channel);
 F2_API int f2_plan_destroy(f2_plan* plan);
 F2_API int f2_plan_channels(const f2_plan* plan);
 /* Warm-up lengths in samples (rounded up to multiples of 256); <= 0 keeps the default that

@@ -332,7 +332,7 @@ def test_chunked_batch_uses_per_utterance_edge_table(gpu, oracle):
         assert np.max(np.abs(a[f0:f1] - b[f0:f1]) / scale) <= 2e-5
 
 
-@pytest.mark.parametrize("fs,C,low,n,dtype", [(44100, 100, 20, 30000, np.float32), (8000, 37, 50, 12345, np.int16),
+@pytest.mark.parametrize("fs,C,low,n,dtype", [(44100, 100, 50, 30000, np.float32), (8000, 37, 50, 12345, np.int16),
                                                (16000, 300, 100, 5000, np.float64)])
 def test_other_filterbanks_and_dtypes(gpu, oracle, fs, C, low, n, dtype):
     """Channel counts that are not multiples of 32 / 128, other sample rates (slower poles ->
@@ -496,3 +496,38 @@ def test_fused_window_store_equals_decimated_frames_plus_gather(gpu, oracle):
         assert np.max(np.abs(win[r0:r0 + nb[u]].cpu().numpy() - wo) / scale[None, None, :]) <= TOL
     with pytest.raises(ValueError):
         batch.run(flat, lpf=True, cutoff=50, dec=True, windows=(offs, dots, win))
+
+
+def test_banks_outside_the_float32_tolerance_raise_instead_of_answering(gpu, oracle, monkeypatch):
+    """make_erb_filters(fs, cf, width) is public API (gammatone/filters.py:89): a bank whose poles sit so
+    close to z = 1 that float32 cannot hold 1e-4 x RMS (LOW_FREQ = 20 Hz, width = 2: the family the
+    round-1 fuzz found at 4.7x the bar, profiles/r01o_fuzz.log) must be an error, not a quiet answer.
+    f2_plan_create predicts the error by running the worst channels on the host in float32 and float64;
+    with the override the prediction is shown to be what the device then does."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import _native, synth
+    fs, C, n = 16000, 96, 4111
+    co = filters.make_erb_filters(fs, filters.centre_freqs(fs, C, 20), 2.0)
+    predicted, channel = engine.bank_check(co)
+    assert predicted > 1.0
+    with pytest.raises(_native.F2Error) as exc:
+        engine.Plan(co)
+    assert exc.value.code == _native.F2_ERR_UNSUPPORTED and "float32" in str(exc.value)
+    with pytest.raises(_native.F2Error):
+        api.erb_filterbank(synth.tone_i16(n, freq=4000.0), co)
+    # the same bank with the check overridden: white noise is fine, the loud stop-band tone is not, and
+    # the prediction was the tone's error
+    monkeypatch.setenv("F2CNN_B200_ALLOW_IMPRECISE", "1")
+    plan = engine.Plan(co)
+    worst = {}
+    for kind, w in (("white", synth.white_noise_i16(n, seed=32)), ("tone", synth.tone_i16(n, freq=fs / 4.0, fs=fs))):
+        go = oracle.erb_filterbank(w, co)
+        gfb = plan.batch([n]).run(torch.from_numpy(w).cuda(), gfb=torch.float64)["gfb"].cpu().numpy().reshape(C, n)
+        scale = np.sqrt(np.mean(go ** 2, axis=1))
+        scale = np.maximum(scale, 0.01 * scale.max())
+        worst[kind] = float((np.max(np.abs(gfb - go), axis=1) / scale).max()) / TOL
+    assert worst["white"] <= 1.0
+    assert worst["tone"] > 1.0 and abs(worst["tone"] - predicted) <= 0.25 * predicted
+    # the configured bank and its neighbours stay far inside
+    for low, width in ((100, 1.0), (100, 2.0), (50, 1.0)):
+        assert engine.bank_check(filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, low), width))[0] < 0.5

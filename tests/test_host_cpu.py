@@ -286,3 +286,18 @@ def test_batched_wav_ingest(tmp_path):
     with pytest.raises(ValueError):
         ingest.read_corpus([paths[0]])
     assert ingest.read_corpus([])[0].numel() == 0
+
+
+def test_bank_check_predicts_the_float32_error_on_the_host():
+    """f2_bank_check needs no device: the configured banks are far inside the tolerance, the family the
+    round-1 fuzz caught (LOW_FREQ = 20 Hz, width = 2; 4.73x measured on the GPU, profiles/r01o_fuzz.log
+    case 32) is predicted at that figure."""
+    from f2cnn_b200 import engine
+    from f2cnn_b200.gammatone import filters
+    for C in (128, 256):
+        pred, _ = engine.bank_check(filters.make_erb_filters(16000, filters.centre_freqs(16000, C, 100)))
+        assert pred < 0.3
+    pred, chan = engine.bank_check(filters.make_erb_filters(16000, filters.centre_freqs(16000, 96, 20), 2.0))
+    assert 4.2 <= pred <= 5.2 and chan >= 93
+    with pytest.raises(ValueError):
+        engine.bank_check(np.zeros((4, 9)))
