@@ -173,9 +173,11 @@ def _pipeline_for(plan, lengths, dots, step, phase, LPF, CUTOFF, src_offsets=Non
 
 
 def release_cached_pipelines():
-    """Drop the cached corpus pipelines (device buffers, pinned staging, worker threads)."""
+    """Drop the cached corpus pipelines (device buffers, pinned staging, worker threads) and the pooled
+    output block."""
     with _pipelines_lock:
         _pipelines.clear()
+    engine.release_host_pool()
 
 
 def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=5, step=160, device_out=False,

@@ -15,6 +15,7 @@
 #include <immintrin.h>
 #include <pthread.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 #include <sys/mman.h>
@@ -220,13 +221,22 @@ int f2_window_runs(const int64_t* centers, const int64_t* counts, const int64_t*
         if (cnt < 0 || n < 0 || (cnt > 0 && !centers))
             return f2_set_error(F2_ERR_INVALID, "f2_window_runs: utterance %d has a negative count or length", u);
         int64_t row = row_offsets ? row_offsets[u] : rows;
-        int64_t prev_frame = -2;
+        int64_t prev_first = INT64_MIN / 2;  // first sample of the previous window IF it extended/opened a run
+        const int64_t last_ok = n - 1 - reach;  // largest centre whose last sample is inside the utterance
+        const int64_t* cen = centers + pos;
         for (int64_t i = 0; i < cnt; ++i, ++row) {
-            const int64_t c = centers[pos + i];
-            const int64_t first = c - reach, last = c + reach;
+            const int64_t c = cen[i];
+            const int64_t first = c - reach;
+            if (first == prev_first + step && c <= last_ok) {
+                // the common case (a label grid): next frame of the same run -- no division, no checks
+                if (runs && nr <= max_runs) runs[nr - 1].count += 1;
+                prev_first = first;
+                continue;
+            }
+            prev_first = INT64_MIN / 2;
             // InputGenerator.py:76 indexes Python lists/arrays: an index in [-n, 0) wraps, anything else
             // outside [0, n) is an IndexError
-            if (last >= n || first < -n)
+            if (c > last_ok || first < -n)
                 return f2_set_error(F2_ERR_INDEX, "index out of bounds: utterance %d, timepoint %lld, %lld samples", u,
                                     (long long)c, (long long)n);
             if (first < 0) {  // wraps around the end: not a block of consecutive frames
@@ -239,18 +249,13 @@ int f2_window_runs(const int64_t* centers, const int64_t* counts, const int64_t*
                 continue;
             }
             if (!strided) continue;
-            const int64_t frame = (first - ph) / step;
-            if (frame == prev_frame + 1 && nr > 0) {
-                if (runs && nr <= max_runs) runs[nr - 1].count += 1;
-            } else {
-                if (runs && nr < max_runs) {
-                    runs[nr].first_frame = frame_offsets[u] + frame;
-                    runs[nr].row0 = row;
-                    runs[nr].count = 1;
-                }
-                ++nr;
+            if (runs && nr < max_runs) {
+                runs[nr].first_frame = frame_offsets[u] + (first - ph) / step;
+                runs[nr].row0 = row;
+                runs[nr].count = 1;
             }
-            prev_frame = frame;
+            ++nr;
+            prev_first = first;
         }
         pos += cnt;
         rows += cnt;

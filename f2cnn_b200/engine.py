@@ -364,7 +364,9 @@ class WindowPipeline:
     on an upload stream at the start, sub-batch i is filtered on the compute stream while the
     frames of sub-batch i-1 travel on a download stream, and each download is followed, in stream
     order, by the host placement of its rows (cudaLaunchHostFunc -> thread pool), so the host
-    never waits between sub-batches.
+    never waits between sub-batches.  Consecutive sub-batches run on two alternating compute
+    streams (each with its own ring workspace), so the tail of one launch overlaps the head of the
+    next.
 
     lengths[u]: samples of utterance u; src_offsets[u]: where it starts in the host buffer passed
     to run() (default: back to back), so a shard can read its utterances out of the buffer that
@@ -387,19 +389,30 @@ class WindowPipeline:
         self.frame_offsets = np.concatenate([[0], np.cumsum(n_dec)]).astype(np.int64)
         self.total_frames = int(self.frame_offsets[-1])
         self.total_samples = int(cum[-1])
-        # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that:
-        # nothing can be placed before the first sub-batch is uploaded, filtered and downloaded
+        # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that (nothing
+        # can be placed before the first sub-batch is uploaded, filtered and downloaded) and the last few
+        # shrink to a quarter (the rows of the last sub-batch are placed after the GPU has gone idle)
         if n_sub is None:
             # a sub-batch should still fill the device: 592 utterances x 4 channel groups = one wave of CTAs
-            n_sub = U // 512
-        n_sub = max(1, min(int(n_sub), 16, max(U, 1)))
+            n_sub = min(U // 576, 8)
+        n_sub = max(1, min(int(n_sub), 32, max(U, 1)))
         per_sub = cum[-1] / n_sub
-        marks, size, at = [0.0], per_sub / 8, 0.0
-        while size > 0 and at + size < cum[-1]:
+        head, size, at = [], per_sub / 8, 0.0
+        while size < per_sub and at + size < cum[-1] / 2:
             at += size
-            marks.append(at)
-            size = min(per_sub, size * 2)
-        cuts = sorted(set([0] + [int(np.searchsorted(cum, m)) for m in marks[1:]] + [U]))
+            head.append(at)
+            size *= 2
+        tail, size, back = [], per_sub / 4, float(cum[-1])
+        while size < per_sub and back - size > cum[-1] / 2:
+            back -= size
+            tail.append(back)
+            size *= 2
+        body = []
+        if back - at > per_sub:
+            k = max(1, int(round((back - at) / per_sub)))
+            body = [at + (back - at) * j / k for j in range(1, k)]
+        marks = head + body + tail[::-1]
+        cuts = sorted(set([0] + [int(np.searchsorted(cum, m)) for m in marks] + [U]))
         dev = plan.device
         C = plan.n_channels
         self.subs = []
@@ -423,6 +436,9 @@ class WindowPipeline:
             self._dec_dev = torch.empty((max(self.total_frames, 1), C), dtype=torch.float32, device=dev)
             self._dec_host = _pinned_empty(max(self.total_frames, 1) * C, torch.float32).view(-1, C)
             self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            # consecutive sub-batches alternate between two compute streams: a launch ends with a tail
+            # of its longest utterances on half-empty SMs, and the next launch's CTAs fill them
+            self._s_comp = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
             self._ev_in = [torch.cuda.Event() for _ in self.subs]
             self._ev_done = [torch.cuda.Event() for _ in self.subs]
         self.placer = placer if placer is not None else Placer()
@@ -455,7 +471,7 @@ class WindowPipeline:
         numpy arrays; runs: (n, 3) int64 from engine.window_runs on this pipeline's frame_offsets;
         out_host: the (N, dots, C) float32 host array or tensor the rows go to (any host memory).
         Returns when every row has been placed."""
-        comp = torch.cuda.current_stream(self.plan.device)
+        caller = torch.cuda.current_stream(self.plan.device)
         dev = self.plan.device
         C = self.plan.n_channels
         listed = isinstance(wave_host, (list, tuple))
@@ -478,8 +494,8 @@ class WindowPipeline:
         per_sub = self._split_runs(runs)
         out_flat = out_host
         esize = self._wave_dev.element_size()
-        self._s_in.wait_stream(comp)
-        self._s_out.wait_stream(comp)
+        for s_ in (self._s_in, self._s_out, self._s_comp[0], self._s_comp[1]):
+            s_.wait_stream(caller)
         if pinned:
             # all uploads are queued at once (444 MB for the corpus): over after the first few ms
             for i, sub in enumerate(self.subs):
@@ -500,6 +516,7 @@ class WindowPipeline:
                 with torch.cuda.stream(self._s_in):
                     self._wave_dev[sub["s0"]:sub["s1"]].copy_(self._stage[sub["s0"]:sub["s1"]], non_blocking=True)
                     self._ev_in[i].record(self._s_in)
+            comp = self._s_comp[i & 1]
             comp.wait_event(self._ev_in[i])
             dec = self._dec_dev[sub["f0"]:sub["f1"]]
             sub["batch"].run(self._wave_dev[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff, out={"dec": dec},
@@ -511,7 +528,8 @@ class WindowPipeline:
                     self._dec_host[sub["f0"]:sub["f1"]].copy_(dec, non_blocking=True)
                 if per_sub[i].shape[0]:
                     self.placer.submit(self._dec_host, per_sub[i], out_flat, dots=self.dots, stream=self._s_out)
-        comp.wait_stream(self._s_out)
+        for s_ in (self._s_out, self._s_comp[0], self._s_comp[1]):
+            caller.wait_stream(s_)
         self._s_out.synchronize()
         self.placer.wait()
         return out_host
@@ -639,11 +657,18 @@ def window_runs(centers, counts, lengths, frame_offsets, radius=5, step=160, pha
             raise IndexError(L.f2_last_error().decode("utf-8", "replace"))
         check(rc)
 
-    call(None, 0)  # count
+    # one pass when the guess holds (a label grid is one run per utterance); the count comes back either way
+    room = int(min(max(centers.shape[0], 1), max(4 * n_utts, 1024)))
+    runs = np.empty((room, 3), dtype=np.int64)
+    try:
+        call(runs, room)
+    except _native.F2Error as e:
+        if e.code != _native.F2_ERR_WORKSPACE:
+            raise
+        runs = np.empty((max(n_runs.value, 1), 3), dtype=np.int64)
+        call(runs, n_runs.value)
     if n_runs.value < 0:
         return None, ph.value, n_rows.value
-    runs = np.empty((max(n_runs.value, 1), 3), dtype=np.int64)
-    call(runs, n_runs.value)
     return runs[:n_runs.value], ph.value, n_rows.value
 
 
@@ -713,19 +738,52 @@ class Placer:
             pass
 
 
+_host_pool = []            # [(address, nbytes)]: freed corpus-sized blocks waiting for the next request
+_host_pool_lock = threading.Lock()
+_HOST_POOL_MIN = 64 << 20  # smaller blocks are not worth keeping
+_HOST_POOL_MAX_BLOCKS = 1
+
+
 class _HostBlock:
+    """Lease on a huge-page advised anonymous mapping (f2_host_alloc).  When the numpy array built on it
+    is garbage collected, a corpus-sized block goes back to a one-entry pool instead of to the kernel:
+    the next request of about that size -- the same call again -- gets memory whose pages are already
+    there (a fresh 7.5 GB mapping costs ~0.1 s of page faults even with huge pages)."""
+
     def __init__(self, nbytes):
-        self.nbytes = max(int(nbytes), 1)
-        self.ptr = ctypes.c_void_p()
-        check(_native.lib().f2_host_alloc(self.nbytes, ctypes.byref(self.ptr)))
+        want = max(int(nbytes), 1)
+        self.ptr = None
+        with _host_pool_lock:
+            for i, (addr, size) in enumerate(_host_pool):
+                if want <= size <= want + (want >> 2):
+                    self.ptr, self.nbytes = ctypes.c_void_p(addr), size
+                    del _host_pool[i]
+                    break
+        if self.ptr is None:
+            self.nbytes = want
+            self.ptr = ctypes.c_void_p()
+            check(_native.lib().f2_host_alloc(self.nbytes, ctypes.byref(self.ptr)))
 
     def __del__(self):
         try:
-            if self.ptr is not None and self.ptr.value:
-                _native.lib().f2_host_free(self.ptr, self.nbytes)
-                self.ptr = None
+            if self.ptr is None or not self.ptr.value:
+                return
+            addr, self.ptr = self.ptr.value, None
+            with _host_pool_lock:
+                if self.nbytes >= _HOST_POOL_MIN and len(_host_pool) < _HOST_POOL_MAX_BLOCKS:
+                    _host_pool.append((addr, self.nbytes))
+                    return
+            _native.lib().f2_host_free(ctypes.c_void_p(addr), self.nbytes)
         except Exception:
             pass
+
+
+def release_host_pool():
+    """Give the pooled output blocks back to the operating system."""
+    with _host_pool_lock:
+        blocks, _host_pool[:] = list(_host_pool), []
+    for addr, size in blocks:
+        _native.lib().f2_host_free(ctypes.c_void_p(addr), size)
 
 
 def host_empty(shape, dtype=np.float32):
@@ -735,6 +793,6 @@ def host_empty(shape, dtype=np.float32):
     dt = np.dtype(dtype)
     nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
     block = _HostBlock(nbytes)
-    buf = (ctypes.c_char * block.nbytes).from_address(block.ptr.value)
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(block.ptr.value)
     buf._f2_block = block  # the mapping lives as long as the ctypes view numpy holds on to
     return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
