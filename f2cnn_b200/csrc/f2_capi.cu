@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/f2cnn_b200.h"
+#include "f2_cnn.cuh"
 #include "f2_edge.cuh"
 #include "f2_fused.cuh"
 #include "f2_label.cuh"
@@ -816,6 +817,18 @@ int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64
     F2_CUDA(f2::launch_prep(pp, hp, stream));
     F2_CUDA(f2::launch_rows_envelope(d_rows, (int)r.rows_pad, xz, op, lpf ? 1 : 0, (float)(-a1), (float)b0, out,
                                      out_dtype, stream));
+    return F2_OK;
+}
+
+int f2_umma_selftest(const void* a, int a_rows, const void* b, int n, int k, int shift, int variant, float* d, int* status,
+                     void* stream) {
+    if (!a || !b || !d || !status || n < 16 || n > 256 || (n & 15) || k < 16 || (k & 15) || shift < 0 ||
+        a_rows < shift + 128 || (a_rows & 7))
+        return fail(F2_ERR_INVALID, "f2_umma_selftest: N a multiple of 16 in [16, 256], K a multiple of 16, "
+                    "a_rows a multiple of 8 and >= shift + 128");
+    if ((size_t)(k / 8) * ((size_t)a_rows + (size_t)n) * 16 > 200 * 1024)
+        return fail(F2_ERR_UNSUPPORTED, "f2_umma_selftest: operands exceed 200 KiB of shared memory");
+    F2_CUDA(f2::launch_umma_selftest(a, a_rows, b, n, k, shift, variant, d, status, (cudaStream_t)stream));
     return F2_OK;
 }
 

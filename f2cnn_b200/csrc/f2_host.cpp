@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -92,7 +93,14 @@ struct Job {
     int64_t n_chunks = 0;
     std::atomic<int64_t> next{0};
     std::atomic<int64_t> done{0};
+    double t_submit = 0.0, t_ready = 0.0;  // trace: monotonic seconds
 };
+
+double now_s() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 constexpr int64_t kChunkRows = 192;  // ~1 MB of output per chunk at 11 x 128 floats per row
 
@@ -160,6 +168,7 @@ struct f2_placer {
     std::deque<std::shared_ptr<Job>> ready;  // runnable jobs (workers share the front one)
     int64_t pending = 0;                     // submitted and not yet finished
     bool stop = false;
+    std::vector<double> trace;               // per finished job: submit, ready, done (seconds), rows
 
     void loop() {
         std::unique_lock<std::mutex> lk(mu);
@@ -177,12 +186,17 @@ struct f2_placer {
             lk.lock();
             if (last) {
                 if (!ready.empty() && ready.front() == j) ready.pop_front();
+                if (trace.size() < 4 * 4096) {
+                    const double t[4] = {j->t_submit, j->t_ready, now_s(), (double)j->cum.back()};
+                    trace.insert(trace.end(), t, t + 4);
+                }
                 if (--pending == 0) cv_idle.notify_all();
             }
         }
     }
     void make_ready(std::shared_ptr<Job> j) {
         std::lock_guard<std::mutex> lk(mu);
+        j->t_ready = now_s();
         if (j->n_chunks == 0) {
             if (--pending == 0) cv_idle.notify_all();
             return;
@@ -320,6 +334,7 @@ int f2_placer_submit(f2_placer* p, int after_stream, void* stream, const float* 
     j->frames = frames, j->out = out, j->C = n_channels, j->dots = dots;
     j->runs.assign(runs, runs + n_runs);
     prepare(*j);
+    j->t_submit = now_s();
     {
         std::lock_guard<std::mutex> lk(p->mu);
         ++p->pending;
@@ -344,6 +359,16 @@ int f2_placer_wait(f2_placer* p) {
     std::unique_lock<std::mutex> lk(p->mu);
     p->cv_idle.wait(lk, [&] { return p->pending == 0; });
     return F2_OK;
+}
+
+int64_t f2_placer_trace(f2_placer* p, double* out, int64_t max_jobs, int clear) {
+    if (!p) return 0;
+    std::lock_guard<std::mutex> lk(p->mu);
+    const int64_t n = std::min<int64_t>((int64_t)p->trace.size() / 4, out ? max_jobs : 0);
+    for (int64_t i = 0; i < 4 * n; ++i) out[i] = p->trace[(size_t)i];
+    const int64_t have = (int64_t)p->trace.size() / 4;
+    if (clear) p->trace.clear();
+    return out ? n : have;
 }
 
 int f2_placer_destroy(f2_placer* p) {

@@ -439,8 +439,12 @@ class WindowPipeline:
             # consecutive sub-batches alternate between two compute streams: a launch ends with a tail
             # of its longest utterances on half-empty SMs, and the next launch's CTAs fill them
             self._s_comp = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-            self._ev_in = [torch.cuda.Event() for _ in self.subs]
-            self._ev_done = [torch.cuda.Event() for _ in self.subs]
+            self._ev_in = [torch.cuda.Event(enable_timing=True) for _ in self.subs]
+            self._ev_done = [torch.cuda.Event(enable_timing=True) for _ in self.subs]
+            self._ev_out = [torch.cuda.Event(enable_timing=True) for _ in self.subs]
+            self._ev_start = torch.cuda.Event(enable_timing=True)
+        self.timing = False     # True: run() synchronises first and keeps a timeline (see timeline())
+        self._t0 = None
         self.placer = placer if placer is not None else Placer()
 
     # -- uploads -------------------------------------------------------------------------------
@@ -494,6 +498,12 @@ class WindowPipeline:
         per_sub = self._split_runs(runs)
         out_flat = out_host
         esize = self._wave_dev.element_size()
+        if self.timing:
+            import time
+            torch.cuda.synchronize(dev)
+            self.placer.trace(clear=True)
+            self._t0 = time.monotonic()
+            self._ev_start.record(caller)
         for s_ in (self._s_in, self._s_out, self._s_comp[0], self._s_comp[1]):
             s_.wait_stream(caller)
         if pinned:
@@ -526,6 +536,7 @@ class WindowPipeline:
                 self._s_out.wait_event(self._ev_done[i])
                 if sub["f1"] > sub["f0"]:
                     self._dec_host[sub["f0"]:sub["f1"]].copy_(dec, non_blocking=True)
+                self._ev_out[i].record(self._s_out)
                 if per_sub[i].shape[0]:
                     self.placer.submit(self._dec_host, per_sub[i], out_flat, dots=self.dots, stream=self._s_out)
         for s_ in (self._s_out, self._s_comp[0], self._s_comp[1]):
@@ -533,6 +544,20 @@ class WindowPipeline:
         self._s_out.synchronize()
         self.placer.wait()
         return out_host
+
+    def timeline(self):
+        """After a run() with timing = True: per sub-batch, milliseconds since the start of the run at
+        which its waves were on the device, its kernels had finished, its frames were on the host (CUDA
+        events), and at which its rows became runnable / were placed (host clock of the worker pool)."""
+        torch.cuda.synchronize(self.plan.device)
+        trace = self.placer.trace(clear=True)
+        rows = []
+        for i, sub in enumerate(self.subs):
+            rows.append(dict(utterances=sub["u1"] - sub["u0"], h2d=self._ev_start.elapsed_time(self._ev_in[i]),
+                             kernels=self._ev_start.elapsed_time(self._ev_done[i]),
+                             d2h=self._ev_start.elapsed_time(self._ev_out[i])))
+        jobs = [dict(runnable=(t[1] - self._t0) * 1e3, placed=(t[2] - self._t0) * 1e3, rows=int(t[3])) for t in trace]
+        return rows, jobs
 
     @property
     def frames_host(self):
@@ -727,6 +752,14 @@ class Placer:
     def wait(self):
         check(_native.lib().f2_placer_wait(self._h))
         self._keep.clear()
+
+    def trace(self, clear=True):
+        """(jobs, 4) float64: submit, runnable, done (CLOCK_MONOTONIC seconds), rows -- per finished job."""
+        L = _native.lib()
+        n = int(L.f2_placer_trace(self._h, None, 0, 0))
+        buf = np.zeros((max(n, 1), 4), dtype=np.float64)
+        n = int(L.f2_placer_trace(self._h, buf.ctypes.data_as(ctypes.c_void_p), n, int(bool(clear))))
+        return buf[:n]
 
     def __del__(self):
         try:

@@ -202,6 +202,10 @@ F2_API int f2_placer_threads(const f2_placer* placer);
 F2_API int f2_placer_submit(f2_placer* placer, int after_stream, void* stream, const float* frames, int n_channels,
                             int dots, const f2_win_run* runs, int64_t n_runs, float* out);
 F2_API int f2_placer_wait(f2_placer* placer);
+/* Trace of the finished jobs, 4 doubles each: submit, runnable, done (CLOCK_MONOTONIC seconds) and the
+ * rows placed.  Returns the number of jobs written (out == NULL: the number recorded); clear != 0
+ * empties the trace. */
+F2_API int64_t f2_placer_trace(f2_placer* placer, double* out, int64_t max_jobs, int clear);
 /* Anonymous host memory advised to use transparent huge pages (a fresh 7.5 GB tensor of 4 KiB pages
  * costs two million page faults on its first write). */
 F2_API int f2_host_alloc(size_t bytes, void** out);
@@ -218,6 +222,14 @@ F2_API int f2_host_free(void* ptr, size_t bytes);
  * arithmetic throughout (the CSV keeps round(a, 5), round(p, 5)). */
 F2_API int f2_label_fit(const double* formant, const int64_t* first, const int32_t* center, int64_t n_items, int dots,
                         int step, double* out, void* stream);
+
+/* ---- CNN forward of `cnn eval*` on the tensor cores ---------------------
+ * Self-test of the tcgen05 operand conventions the CNN kernels rest on: D[r][j] = sum_k A[shift+r][k] *
+ * B[j][k] for r < 128, A [a_rows][K] and B [N][K] row-major bf16 (device), D [128][N] float32 (device),
+ * *status (device int) != 0 when the tensor-core pipeline did not complete.  variant 0 is the layout in
+ * use; variant 1 swaps the descriptor's leading / stride offsets and must give a different result. */
+F2_API int f2_umma_selftest(const void* a, int a_rows, const void* b, int n, int k, int shift, int variant, float* d,
+                            int* status, void* stream);
 
 /* Host -> device upload of n_spans byte ranges on `stream` (cudaMemcpyAsync each): the utterances of a
  * shard picked out of one host buffer that holds the whole corpus.  src_host should be page-locked
