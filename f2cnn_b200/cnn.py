@@ -3,12 +3,22 @@ for the `cnn eval*` path: Conv32 3x3 same -> Conv32 3x3 -> MaxPool2 -> Conv64 3x
 Conv64 3x3 -> MaxPool2 -> Flatten(1920) -> Dense516 -> Dense2 softmax, ReLU after every conv /
 the first dense, dropout inactive at inference.
 
-This is a consumer of the hot path, not part of it: the
-convolutions go through cuDNN as plain library calls.  No trained model ships with the
-reference and Keras is not installed here, so weights are either seeded (benchmarks, tests) or
-loaded from arrays in Keras layout with `load_keras_arrays`."""
+Two implementations of the same network:
+  * TensorCoreCNN -- the product path of `cnn eval*`: hand-written tcgen05 kernels in
+    libf2cnn_b200.so (csrc/f2_cnn.cu: implicit-GEMM convolutions with the accumulators in tensor
+    memory, bf16 operands, float32 accumulation), fed straight from the time-major envelope.
+  * F2CNN -- a plain PyTorch module (float32 through cuDNN).  It is the ORACLE the kernels are tested
+    against (there is no Keras here and no trained model ships with the reference) and the carrier of
+    the parameters: weights are seeded (benchmarks, tests) or loaded from arrays in Keras layout with
+    `load_keras_arrays`."""
+import ctypes
+
+import numpy as np
 import torch
 import torch.nn.functional as F
+
+from . import _native
+from ._native import check
 
 
 class F2CNN(torch.nn.Module):
@@ -79,3 +89,94 @@ def predict(model, frames_dev, batch=8192, autocast_dtype=None, channels_last=Fa
         else:
             out.append(model(x))
     return torch.cat(out) if out else torch.zeros((0, 2), device=frames_dev.device)
+
+
+class TensorCoreCNN:
+    """The network on the 5th-generation tensor cores (f2_cnn_* of the C ABI).  `source`: an F2CNN
+    module or the 12 arrays of Keras' model.get_weights() (conv kernels HWIO, dense kernels (in, out))."""
+
+    def __init__(self, source, device=None, dots=11, channels=128):
+        if not torch.cuda.is_available():
+            raise RuntimeError("TensorCoreCNN needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        arrays = keras_arrays(source) if isinstance(source, torch.nn.Module) else list(source)
+        if len(arrays) != 12:
+            raise ValueError("expected the 12 parameter arrays of the reference network, got %d" % len(arrays))
+        shapes = [(3, 3, 1, 32), (32,), (3, 3, 32, 32), (32,), (3, 3, 32, 64), (64,), (3, 3, 64, 64), (64,),
+                  (1920, 516), (516,), (516, 2), (2,)]
+        host = []
+        for a, shp in zip(arrays, shapes):
+            a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+            if a.shape != shp:
+                raise ValueError("parameter of shape %s where the reference network has %s" % (a.shape, shp))
+            host.append(a)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        ptrs = (ctypes.c_void_p * 12)(*[a.ctypes.data for a in host])
+        self._h = ctypes.c_void_p()
+        check(_native.lib().f2_cnn_create(self.device.index, ptrs, int(dots), int(channels), ctypes.byref(self._h)))
+        self._ws = None
+        self.step = None
+
+    def __del__(self):
+        try:
+            h = getattr(self, "_h", None)
+            if h is not None and h.value:
+                _native.lib().f2_cnn_destroy(h)
+                self._h = None
+        except Exception:
+            pass
+
+    def predict_envelope(self, env_t, step=160, frames=None, stream=None):
+        """Scores of the stride-1 frames of a time-major envelope ([n, 128] float32 on the device):
+        frame i = rows i + k*step, k < 11, normalised per frame like Training.normalizeInput
+        (Evaluating.py:70-87).  Returns an (n_frames, 2) float32 device tensor; raises ValueError where
+        normalizeInput would (a value <= 0)."""
+        if env_t.dtype != torch.float32 or not env_t.is_contiguous() or env_t.dim() != 2 or env_t.shape[1] != 128 \
+                or env_t.device != self.device:
+            raise ValueError("env_t: contiguous float32 [n, 128] tensor on %s" % self.device)
+        n = int(env_t.shape[0])
+        nb = max(n - 11 * int(step), 0)
+        i0, i1 = (0, nb) if frames is None else (int(frames[0]), int(frames[1]))
+        if not 0 <= i0 <= i1 <= nb:
+            raise IndexError("frames=(%d, %d) outside the %d frames of this envelope" % (i0, i1, nb))
+        scores = torch.empty((i1 - i0, 2), dtype=torch.float32, device=self.device)
+        if i1 == i0:
+            return scores
+        L = _native.lib()
+        need = int(L.f2_cnn_workspace_bytes(self._h, i1 - i0))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        flags = torch.zeros(2, dtype=torch.int32, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(L.f2_cnn_forward(self._h, ctypes.c_void_p(env_t.data_ptr()), n, int(step), i0, i1,
+                               ctypes.c_void_p(scores.data_ptr()), ctypes.c_void_p(flags.data_ptr()),
+                               ctypes.c_void_p(self._ws.data_ptr()), self._ws.numel(), ctypes.c_void_p(s.cuda_stream)))
+        bad, status = (int(v) for v in flags.tolist())
+        if status:
+            raise RuntimeError("tensor-core pipeline did not complete (stage %d)" % status)
+        if bad:
+            raise ValueError("values must all be positive")  # Training.py:18-20
+        return scores
+
+    def intermediates(self, n_frames):
+        """(pooled conv2 output (n, 32, 4, 63), features (n, 1920)) of the last chunk, as float32 -- for
+        the layer-by-layer tests (n_frames <= 8192 so that the chunk is the whole call)."""
+        chunk, off = ctypes.c_int64(), ctypes.c_size_t()
+        check(_native.lib().f2_cnn_workspace_layout(int(n_frames), ctypes.byref(chunk), ctypes.byref(off)))
+        base = (self._ws.data_ptr() + 255) // 256 * 256 - self._ws.data_ptr()
+        raw = self._ws[base:base + n_frames * 4 * 252 * 16].view(torch.bfloat16).view(n_frames, 4, 252, 8)
+        pooled = raw.permute(0, 1, 3, 2).reshape(n_frames, 32, 4, 63).float()
+        feat = self._ws[base + off.value:base + off.value + n_frames * 1920 * 2].view(torch.bfloat16).view(n_frames, 1920)
+        return pooled, feat.float()
+
+
+def keras_arrays(model):
+    """The parameters of an F2CNN module in Keras' get_weights() order and layout."""
+    out = []
+    for conv in (model.c1, model.c2, model.c3, model.c4):
+        out.append(conv.weight.detach().float().permute(2, 3, 1, 0).contiguous().cpu().numpy())
+        out.append(conv.bias.detach().float().cpu().numpy())
+    for lin in (model.d1, model.d2):
+        out.append(lin.weight.detach().float().t().contiguous().cpu().numpy())
+        out.append(lin.bias.detach().float().cpu().numpy())
+    return out

@@ -820,6 +820,155 @@ int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64
     return F2_OK;
 }
 
+// ---- CNN forward ----------------------------------------------------------------------------------
+struct f2_cnn {
+    int device = 0;
+    int sm_count = 148;
+    void* blob = nullptr;  // one allocation holding every packed parameter
+    f2::CnnWeights w{};
+};
+
+namespace {
+constexpr long long kCnnChunkFrames = 8192;
+
+uint16_t bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN stays NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// Keras conv kernel HWIO [3][3][cin][cout] -> [tap][cin / 8][cout][8] bf16
+void pack_conv(const float* k, int cin, int cout, uint16_t* out) {
+    for (int tap = 0; tap < 9; ++tap)
+        for (int p = 0; p < cin / 8; ++p)
+            for (int n = 0; n < cout; ++n)
+                for (int j = 0; j < 8; ++j)
+                    out[(((size_t)tap * (cin / 8) + p) * cout + n) * 8 + j] = bf16_rne(k[((size_t)tap * cin + 8 * p + j) * cout + n]);
+}
+}  // namespace
+
+int f2_cnn_create(int device, const float* const* arrays, int dots, int channels, f2_cnn** out) {
+    if (!arrays || !out) return fail(F2_ERR_INVALID, "f2_cnn_create: null arguments");
+    for (int i = 0; i < 12; ++i)
+        if (!arrays[i]) return fail(F2_ERR_INVALID, "f2_cnn_create: parameter array %d is null", i);
+    if (dots != 11 || channels != 128)
+        return fail(F2_ERR_UNSUPPORTED, "f2_cnn_create: the tensor-core kernels are built for the configured front end "
+                    "(RADIUS = 5 -> 11 dots, 128 channels), got %d x %d", dots, channels);
+    int ndev = 0;
+    F2_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(F2_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(F2_ERR_CUDA, "cannot select device %d", device);
+    cudaDeviceProp prop;
+    F2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(F2_ERR_UNSUPPORTED, "device %d is sm_%d%d; tcgen05 needs sm_100a", device, prop.major, prop.minor);
+    // Keras order: conv kernels HWIO + biases (Training.py:95-108), dense kernels (in, out) + biases (:111-114)
+    const float *k1 = arrays[0], *b1 = arrays[1], *k2 = arrays[2], *b2 = arrays[3], *k3 = arrays[4], *b3 = arrays[5],
+                *k4 = arrays[6], *b4 = arrays[7], *W5 = arrays[8], *b5 = arrays[9], *W6 = arrays[10], *b6 = arrays[11];
+    const size_t n_w1 = 2 * 32 * 8, n_w2 = 9 * 4 * 32 * 8, n_w3 = 9 * 4 * 64 * 8, n_w4 = 9 * 8 * 64 * 8;
+    const size_t n_w5 = (size_t)3 * 30 * 8 * 176 * 8;
+    const size_t bf_total = n_w1 + n_w2 + n_w3 + n_w4 + n_w5;
+    const size_t f_total = 32 + 32 + 64 + 64 + 516 + 516 * 2 + 2;
+    std::vector<uint16_t> hb(bf_total, 0);
+    std::vector<float> hf(f_total);
+    uint16_t* w1 = hb.data();
+    uint16_t* w2 = w1 + n_w1;
+    uint16_t* w3 = w2 + n_w2;
+    uint16_t* w4 = w3 + n_w3;
+    uint16_t* w5 = w4 + n_w4;
+    for (int n = 0; n < 32; ++n) {
+        for (int j = 0; j < 8; ++j) w1[(size_t)n * 8 + j] = bf16_rne(k1[(size_t)j * 32 + n]);      // taps 0..7 (cin = 1)
+        w1[(size_t)(32 + n) * 8] = bf16_rne(k1[(size_t)8 * 32 + n]);                                 // tap 8, then zeros
+    }
+    pack_conv(k2, 32, 32, w2);
+    pack_conv(k3, 32, 64, w3);
+    pack_conv(k4, 64, 64, w4);
+    for (int pass = 0; pass < 3; ++pass)
+        for (int kc = 0; kc < 30; ++kc)
+            for (int p = 0; p < 8; ++p)
+                for (int nn = 0; nn < 176; ++nn) {
+                    const int n = pass * 176 + nn;
+                    if (n >= 516) continue;
+                    for (int j = 0; j < 8; ++j)
+                        w5[((((size_t)pass * 30 + kc) * 8 + p) * 176 + nn) * 8 + j] = bf16_rne(W5[(size_t)(kc * 64 + 8 * p + j) * 516 + n]);
+                }
+    float* f = hf.data();
+    memcpy(f, b1, 32 * 4);
+    memcpy(f + 32, b2, 32 * 4);
+    memcpy(f + 64, b3, 64 * 4);
+    memcpy(f + 128, b4, 64 * 4);
+    memcpy(f + 192, b5, 516 * 4);
+    memcpy(f + 708, W6, 516 * 2 * 4);
+    memcpy(f + 1740, b6, 2 * 4);
+    f2_cnn* c = new (std::nothrow) f2_cnn();
+    if (!c) return fail(F2_ERR_INVALID, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    const size_t bf_bytes = align_up(bf_total * 2, 256);
+    cudaError_t e = cudaMalloc(&c->blob, bf_bytes + f_total * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(c->blob, hb.data(), bf_total * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((char*)c->blob + bf_bytes, hf.data(), f_total * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (c->blob) cudaFree(c->blob);
+        delete c;
+        return fail(F2_ERR_CUDA, "cnn parameter upload: %s", cudaGetErrorString(e));
+    }
+    const uint8_t* b = (const uint8_t*)c->blob;
+    c->w.w1 = b;
+    c->w.w2 = c->w.w1 + n_w1 * 2;
+    c->w.w3 = c->w.w2 + n_w2 * 2;
+    c->w.w4 = c->w.w3 + n_w3 * 2;
+    c->w.w5 = c->w.w4 + n_w4 * 2;
+    const float* df = (const float*)(b + bf_bytes);
+    c->w.b1 = df;
+    c->w.b2 = df + 32;
+    c->w.b3 = df + 64;
+    c->w.b4 = df + 128;
+    c->w.b5 = df + 192;
+    c->w.w6 = df + 708;
+    c->w.b6 = df + 1740;
+    *out = c;
+    return F2_OK;
+}
+
+int f2_cnn_destroy(f2_cnn* c) {
+    if (!c) return F2_OK;
+    DeviceGuard guard(c->device);
+    if (c->blob) cudaFree(c->blob);
+    delete c;
+    return F2_OK;
+}
+
+size_t f2_cnn_workspace_bytes(const f2_cnn* c, int64_t n_frames) {
+    if (!c || n_frames <= 0) return 256;
+    return f2::cnn_workspace_bytes(std::min<long long>(n_frames, kCnnChunkFrames));
+}
+
+int f2_cnn_workspace_layout(int64_t n_frames, int64_t* chunk_frames, size_t* features_offset) {
+    const long long chunk = std::max<long long>(1, std::min<long long>(n_frames, kCnnChunkFrames));
+    if (chunk_frames) *chunk_frames = chunk;
+    if (features_offset) *features_offset = align_up((size_t)chunk * 4 * 252 * 16, 256);
+    return F2_OK;
+}
+
+int f2_cnn_forward(f2_cnn* c, const float* env_t, int64_t n_rows, int step, int64_t i0, int64_t i1, float* scores,
+                   int* flags, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!c) return fail(F2_ERR_INVALID, "f2_cnn_forward: null network");
+    if (i1 <= i0) return F2_OK;
+    if (!env_t || !scores || !flags || step <= 0 || i0 < 0 || i1 + (int64_t)10 * step > n_rows)
+        return fail(F2_ERR_INVALID, "f2_cnn_forward: frames [%lld, %lld) x 11 dots of step %d leave the %lld envelope rows",
+                    (long long)i0, (long long)i1, step, (long long)n_rows);
+    const size_t need = f2_cnn_workspace_bytes(c, i1 - i0);
+    if (!workspace || workspace_bytes < need) return fail(F2_ERR_WORKSPACE, "workspace %zu bytes, need %zu", workspace_bytes, need);
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(F2_ERR_CUDA, "cannot select device %d", c->device);
+    F2_CUDA(f2::launch_cnn_forward(c->w, env_t, step, i0, i1 - i0, std::min<long long>(i1 - i0, kCnnChunkFrames), scores, flags,
+                                   flags + 1, workspace, c->sm_count, (cudaStream_t)stream));
+    return F2_OK;
+}
+
 int f2_umma_selftest(const void* a, int a_rows, const void* b, int n, int k, int shift, int variant, float* d, int* status,
                      void* stream) {
     if (!a || !b || !d || !status || n < 16 || n > 256 || (n & 15) || k < 16 || (k & 15) || shift < 0 ||

@@ -224,7 +224,30 @@ F2_API int f2_label_fit(const double* formant, const int64_t* first, const int32
                         int step, double* out, void* stream);
 
 /* ---- CNN forward of `cnn eval*` on the tensor cores ---------------------
- * Self-test of the tcgen05 operand conventions the CNN kernels rest on: D[r][j] = sum_k A[shift+r][k] *
+ * The reference network (scripts/CNN/Training.py:93-114): Conv32 3x3 same, Conv32 3x3, MaxPool2, Conv64 3x3
+ * same, Conv64 3x3, MaxPool2, Flatten(1920), Dense516, Dense2 softmax, ReLU after each convolution and the
+ * first dense layer -- evaluated on every stride-1 frame of an utterance (Evaluating.py:70-87: frame i =
+ * envelope samples i + k*STEP, k < 11, normalizeInput per frame, model.predict).  Here: three tcgen05
+ * kernels, bf16 operands with float32 accumulation in tensor memory, frames taken straight from the
+ * time-major envelope (`env_t` of f2_batch_run), so the (frames, 11, 128) tensor is never materialised.
+ * arrays: 12 HOST float32 pointers in Keras' get_weights() order -- conv kernels HWIO and biases of the
+ * four convolutions, then the two dense kernels (in, out) and biases.  Only the configured geometry
+ * (dots = 11, channels = 128) is built; anything else fails with F2_ERR_UNSUPPORTED. */
+typedef struct f2_cnn f2_cnn;
+F2_API int f2_cnn_create(int device, const float* const* arrays, int dots, int channels, f2_cnn** out);
+F2_API int f2_cnn_destroy(f2_cnn* cnn);
+F2_API size_t f2_cnn_workspace_bytes(const f2_cnn* cnn, int64_t n_frames);
+/* Frames i0 <= i < i1 of env_t ([n_rows][128] float32, device); scores: [i1 - i0][2] float32 softmax
+ * (falling, rising), device.  flags: two device ints the caller zeroes: flags[0] != 0 afterwards when a
+ * frame held a value <= 0 (Training.normalizeInput raises ValueError there), flags[1] != 0 when the
+ * tensor-core pipeline did not complete.  Frames are processed in chunks through `workspace`. */
+F2_API int f2_cnn_forward(f2_cnn* cnn, const float* env_t, int64_t n_rows, int step, int64_t i0, int64_t i1, float* scores,
+                          int* flags, void* workspace, size_t workspace_bytes, void* stream);
+/* Where the intermediate tensors of the LAST chunk sit in the workspace (tests compare them layer by layer):
+ * pooled conv2 output at the aligned start, [frame][4 planes][4*63 pixels][8 channels] bf16; the 1920
+ * features per frame (Keras flatten order) as bf16 at *features_offset. */
+F2_API int f2_cnn_workspace_layout(int64_t n_frames, int64_t* chunk_frames, size_t* features_offset);
+/* Self-test of the tcgen05 operand conventions the CNN kernels rest on: D[r][j] = sum_k A[shift+r][k] *
  * B[j][k] for r < 128, A [a_rows][K] and B [N][K] row-major bf16 (device), D [128][N] float32 (device),
  * *status (device int) != 0 when the tensor-core pipeline did not complete.  variant 0 is the layout in
  * use; variant 1 swaps the descriptor's leading / stride offsets and must give a different result. */
