@@ -160,7 +160,7 @@ class TensorCoreCNN:
 
     def intermediates(self, n_frames):
         """(pooled conv2 output (n, 32, 4, 63), features (n, 1920)) of the last chunk, as float32 -- for
-        the layer-by-layer tests (n_frames <= 8192 so that the chunk is the whole call)."""
+        the layer-by-layer tests (n_frames <= 32768 so that the chunk is the whole call)."""
         chunk, off = ctypes.c_int64(), ctypes.c_size_t()
         check(_native.lib().f2_cnn_workspace_layout(int(n_frames), ctypes.byref(chunk), ctypes.byref(off)))
         base = (self._ws.data_ptr() + 255) // 256 * 256 - self._ws.data_ptr()

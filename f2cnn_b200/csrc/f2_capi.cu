@@ -829,7 +829,7 @@ struct f2_cnn {
 };
 
 namespace {
-constexpr long long kCnnChunkFrames = 8192;
+constexpr long long kCnnChunkFrames = 32768;
 
 uint16_t bf16_rne(float f) {
     uint32_t u;

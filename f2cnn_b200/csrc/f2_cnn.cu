@@ -67,19 +67,33 @@ struct FrontSmem {
     static constexpr int total = c1 + 4 * kRowsC1 * 16;
 };
 
-__global__ void __launch_bounds__(128, 1)
+// Warp roles (front and mid kernels): 16 WORKER warps stage operands and drain accumulators -- warp w reads
+// TMEM lanes 32*(w % 4) .., the four warps of a lane quarter share the tiles / columns -- and one ISSUER warp
+// does nothing but feed the tensor core (tcgen05.mma from its elected lane).  The two sides meet only on
+// mbarriers, never on a CTA-wide barrier, so the issuer can run ahead of the epilogues.
+constexpr int kWorkers = 512;
+constexpr int kThreads = kWorkers + 32;
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 cnn_front_kernel(const float* __restrict__ env_t, int step, long long frame0, int n_frames, const uint8_t* __restrict__ w1p,
                  const uint8_t* __restrict__ w2p, const float* __restrict__ b1, const float* __restrict__ b2,
                  uint8_t* __restrict__ pooled2, int* __restrict__ bad_flag, int* __restrict__ status) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ __align__(8) uint64_t bar[2];   // issuer -> workers: conv1 / conv2 of the current frame have completed
+    __shared__ __align__(8) uint64_t rdy[2];   // workers -> issuer: patch matrix staged + TMEM drained / conv1 output written
     __shared__ uint32_t tmem_slot;
-    __shared__ float red[8];
+    __shared__ float red[32];
     __shared__ float s_b1[32], s_b2[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    copy_to_smem(smem + FrontSmem::w1, w1p, 2 * 32 * 16, tid, 128);
-    copy_to_smem(smem + FrontSmem::w2, w2p, 9 * 4 * 32 * 16, tid, 128);
-    for (int i = tid; i < (FrontSmem::total - FrontSmem::g0) / 16; i += 128)
+    const int quarter = warp & 3, group = warp >> 2;
+    copy_to_smem(smem + FrontSmem::w1, w1p, 2 * 32 * 16, tid, kThreads);
+    copy_to_smem(smem + FrontSmem::w2, w2p, 9 * 4 * 32 * 16, tid, kThreads);
+    for (int i = tid; i < (FrontSmem::total - FrontSmem::g0) / 16; i += kThreads)
         reinterpret_cast<uint4*>(smem + FrontSmem::g0)[i] = make_uint4(0, 0, 0, 0);   // halo, slack rows
     if (tid < 32) {
         s_b1[tid] = b1[tid];
@@ -89,162 +103,211 @@ cnn_front_kernel(const float* __restrict__ env_t, int step, long long frame0, in
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&rdy[0], kWorkers);
+        mbar_init(&rdy[1], kWorkers);
         mbar_fence_init();
     }
+    umma::fence_smem_to_async();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const uint32_t s_base = smem_u32(smem);
-    __nv_bfloat16* g0 = reinterpret_cast<__nv_bfloat16*>(smem + FrontSmem::g0);
-    const unsigned short* g0u = reinterpret_cast<const unsigned short*>(smem + FrontSmem::g0);
     constexpr uint32_t kPlaneA1 = kRows1 * 16, kPlaneC1 = kRowsC1 * 16;
     const uint32_t idesc32 = umma::instr_desc_bf16(128, 32);
     uint32_t phase = 0;
     bool alive = true;
 
-    // normalizeInput (Training.py:13-28) of frame f into the padded grid, then the 9-tap patch matrix
-    auto stage_input = [&](int f) {
-        const float* src = env_t + (size_t)(frame0 + f) * kChan + tid;
-        float v[kDots];
-        float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < kDots; ++k) {
-            v[k] = __ldg(src + (size_t)k * (size_t)step * kChan);
-            lo = fminf(lo, v[k]);
-            hi = fmaxf(hi, v[k]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
-        __syncthreads();   // `red` of the previous frame has been read by everybody
-        if (lane == 0) {
-            red[warp] = lo;
-            red[4 + warp] = hi;
-        }
-        __syncthreads();
-        lo = fminf(fminf(red[0], red[1]), fminf(red[2], red[3]));
-        hi = fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]));
-        if (!(lo > 0.f) && tid == 0) atomicOr(bad_flag, 1);   // the reference raises ValueError
-        const float llo = logf(lo), inv = hi > lo ? 1.0f / (logf(hi) - llo) : 0.f;
-#pragma unroll
-        for (int k = 0; k < kDots; ++k)
-            g0[(k + 1) * kW0 + tid + 1] = __float2bfloat16(hi > lo ? (logf(v[k]) - llo) * inv : 0.f);
-        __syncthreads();
-        for (int q = tid; q < kRows1; q += 128) {
-            unsigned short t[9];
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) t[dy * 3 + dx] = g0u[q + dy * kW0 + dx];
-            uint4 p0, p1;
-            p0.x = (uint32_t)t[0] | ((uint32_t)t[1] << 16);
-            p0.y = (uint32_t)t[2] | ((uint32_t)t[3] << 16);
-            p0.z = (uint32_t)t[4] | ((uint32_t)t[5] << 16);
-            p0.w = (uint32_t)t[6] | ((uint32_t)t[7] << 16);
-            p1 = make_uint4((uint32_t)t[8], 0, 0, 0);
-            *reinterpret_cast<uint4*>(smem + FrontSmem::a1 + (size_t)q * 16) = p0;
-            *reinterpret_cast<uint4*>(smem + FrontSmem::a1 + kPlaneA1 + (size_t)q * 16) = p1;
-        }
-        umma::fence_smem_to_async();
-    };
-
-    int f = blockIdx.x;
-    if (f < n_frames) stage_input(f);
-    for (; f < n_frames && alive; f += gridDim.x) {
-        umma::fence_before_sync();
-        __syncthreads();
-        // ---- conv1: 12 tiles x (M128, N32, K16) ----
-        if (tid == 0) {
+    if (warp == kWorkers / 32) {
+        // ================================ issuer warp ================================
+        const uint64_t da1 = umma::smem_desc(s_base + FrontSmem::a1, kPlaneA1, 128);
+        const uint64_t db1 = umma::smem_desc(s_base + FrontSmem::w1, 32 * 16, 128);
+        const uint64_t dc1 = umma::smem_desc(s_base + FrontSmem::c1, kPlaneC1, 128);
+        const uint64_t db2 = umma::smem_desc(s_base + FrontSmem::w2, 512, 128);
+        for (int f = blockIdx.x; f < n_frames && alive; f += gridDim.x) {
+            // ---- conv1: 12 tiles x (M128, N32, K16) ----
+            alive = umma::mbar_wait_bounded(&rdy[0], phase);
             umma::fence_after_sync();
-            for (int t = 0; t < kTiles1; ++t) {
-                const uint64_t da = umma::smem_desc(s_base + FrontSmem::a1 + (uint32_t)t * 128u * 16u, kPlaneA1, 128);
-                const uint64_t db = umma::smem_desc(s_base + FrontSmem::w1, 32 * 16, 128);
-                umma::mma_bf16(tmem + (uint32_t)t * 32u, da, db, idesc32, false);
-            }
-            umma::mma_commit(&bar[0]);
-        }
-        alive = umma::mbar_wait_bounded(&bar[0], phase);
-        umma::fence_after_sync();
-        if (!alive) break;
-        // ---- epilogue 1: bias + relu -> bf16 planes, rows re-strided from 130 to 128 ----
-        for (int t = 0; t < kTiles1; ++t) {
-            float v[32];
-            umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * 32u, v);
-            const int q = t * 128 + warp * 32 + lane;
-            const int y = q / kW0, x = q - y * kW0;
-            if (y < kDots && x < kChan) {
-                uint8_t* dst = smem + FrontSmem::c1 + (size_t)(y * kChan + x) * 16;
+            if (!alive) break;
+            if (umma::elect_one()) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 o;
-                    o.x = pack_bf16(fmaxf(v[8 * j + 0] + s_b1[8 * j + 0], 0.f), fmaxf(v[8 * j + 1] + s_b1[8 * j + 1], 0.f));
-                    o.y = pack_bf16(fmaxf(v[8 * j + 2] + s_b1[8 * j + 2], 0.f), fmaxf(v[8 * j + 3] + s_b1[8 * j + 3], 0.f));
-                    o.z = pack_bf16(fmaxf(v[8 * j + 4] + s_b1[8 * j + 4], 0.f), fmaxf(v[8 * j + 5] + s_b1[8 * j + 5], 0.f));
-                    o.w = pack_bf16(fmaxf(v[8 * j + 6] + s_b1[8 * j + 6], 0.f), fmaxf(v[8 * j + 7] + s_b1[8 * j + 7], 0.f));
-                    *reinterpret_cast<uint4*>(dst + (size_t)j * kPlaneC1) = o;
+                for (int t = 0; t < kTiles1; ++t) umma::mma_bf16(tmem + (uint32_t)t * 32u, da1 + (uint64_t)(t * 128), db1, idesc32, false);
+                umma::mma_commit(&bar[0]);
+            }
+            __syncwarp();
+            // ---- conv2: 9 tiles x 9 taps x 2 x (M128, N32, K16), taps are descriptor shifts ----
+            alive = umma::mbar_wait_bounded(&rdy[1], phase);
+            umma::fence_after_sync();
+            if (!alive) break;
+            if (umma::elect_one()) {
+#pragma unroll 1
+                for (int y = 0; y < kTiles2; ++y) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t shift = (uint32_t)(y * kChan + (tap / 3) * kChan + (tap % 3));
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
+                            umma::mma_bf16(tmem + (uint32_t)y * 32u, dc1 + (uint64_t)(shift + (uint32_t)(2 * kk) * (kPlaneC1 / 16)),
+                                           db2 + (uint64_t)((tap * 2048 + 2 * kk * 512) / 16), idesc32, tap > 0 || kk > 0);
+                    }
+                }
+                umma::mma_commit(&bar[1]);
+            }
+            __syncwarp();
+            phase ^= 1;
+        }
+        if (!alive && lane == 0) atomicExch(status, 1);
+    } else {
+        // ================================ worker warps ================================
+        __nv_bfloat16* g0 = reinterpret_cast<__nv_bfloat16*>(smem + FrontSmem::g0);
+        const unsigned short* g0u = reinterpret_cast<const unsigned short*>(smem + FrontSmem::g0);
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        // The envelope samples of a frame are fetched one whole iteration before they are needed (global
+        // latency is far longer than anything four warps per scheduler can hide): this thread holds channel
+        // c, dots k0, k0 + 4, k0 + 8 of the NEXT frame to be staged.
+        const int c = tid & 127, k0 = tid >> 7;
+        float v[3] = {1.f, 1.f, 1.f};
+        auto fetch_input = [&](int f) {
+            const float* src = env_t + (size_t)(frame0 + f) * kChan + c;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int k = k0 + 4 * j;
+                if (k < kDots) v[j] = __ldg(src + (size_t)k * (size_t)step * kChan);
+            }
+        };
+        // normalizeInput (Training.py:13-28) of the fetched frame into the padded grid, then the 9-tap patch matrix
+        auto stage_input = [&]() {
+            float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (k0 + 4 * j < kDots) {
+                    lo = fminf(lo, v[j]);
+                    hi = fmaxf(hi, v[j]);
                 }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            worker_sync();   // `red` of the previous frame has been read by everybody
+            if (lane == 0) {
+                red[warp] = lo;
+                red[16 + warp] = hi;
+            }
+            worker_sync();
+            lo = red[lane & 15];
+            hi = red[16 + (lane & 15)];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (!(lo > 0.f) && tid == 0) atomicOr(bad_flag, 1);   // the reference raises ValueError
+            const float llo = logf(lo), inv = hi > lo ? 1.0f / (logf(hi) - llo) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int k = k0 + 4 * j;
+                if (k < kDots) g0[(k + 1) * kW0 + c + 1] = __float2bfloat16(hi > lo ? (logf(v[j]) - llo) * inv : 0.f);
+            }
+            worker_sync();
+            for (int q = tid; q < kRows1; q += kWorkers) {
+                unsigned short t[9];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) t[dy * 3 + dx] = g0u[q + dy * kW0 + dx];
+                uint4 p0, p1;
+                p0.x = (uint32_t)t[0] | ((uint32_t)t[1] << 16);
+                p0.y = (uint32_t)t[2] | ((uint32_t)t[3] << 16);
+                p0.z = (uint32_t)t[4] | ((uint32_t)t[5] << 16);
+                p0.w = (uint32_t)t[6] | ((uint32_t)t[7] << 16);
+                p1 = make_uint4((uint32_t)t[8], 0, 0, 0);
+                *reinterpret_cast<uint4*>(smem + FrontSmem::a1 + (size_t)q * 16) = p0;
+                *reinterpret_cast<uint4*>(smem + FrontSmem::a1 + kPlaneA1 + (size_t)q * 16) = p1;
+            }
+            umma::fence_smem_to_async();
+        };
+
+        int f = blockIdx.x;
+        if (f < n_frames) {
+            fetch_input(f);
+            stage_input();
+            if (f + (int)gridDim.x < n_frames) fetch_input(f + gridDim.x);
+            umma::fence_before_sync();
+            mbar_arrive(&rdy[0]);
         }
-        umma::fence_smem_to_async();
-        umma::fence_before_sync();
-        __syncthreads();
-        // ---- conv2: 9 tiles x 9 taps x 2 x (M128, N32, K16), taps are descriptor shifts ----
-        if (tid == 0) {
+        for (; f < n_frames && alive; f += gridDim.x) {
+            alive = umma::mbar_wait_bounded(&bar[0], phase);
             umma::fence_after_sync();
-            for (int y = 0; y < kTiles2; ++y) {
-                bool acc = false;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t shift = (uint32_t)(y * kChan + (tap / 3) * kChan + (tap % 3));
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const uint64_t da = umma::smem_desc(s_base + FrontSmem::c1 + (uint32_t)(2 * kk) * kPlaneC1 + shift * 16u,
-                                                            kPlaneC1, 128);
-                        const uint64_t db = umma::smem_desc(s_base + FrontSmem::w2 + (uint32_t)tap * 2048u + (uint32_t)(2 * kk) * 512u,
-                                                            512, 128);
-                        umma::mma_bf16(tmem + (uint32_t)y * 32u, da, db, idesc32, acc);
-                        acc = true;
+            if (!alive) break;
+            // ---- epilogue 1: bias + relu -> bf16 planes, rows re-strided from 130 to 128 ----
+#pragma unroll 1
+            for (int t = group; t < kTiles1; t += 4) {
+                float a[32];
+                umma::tmem_ld32(tmem + lane_addr + (uint32_t)t * 32u, a);
+                const int q = t * 128 + quarter * 32 + lane;
+                const int y = q / kW0, x = q - y * kW0;
+                if (y < kDots && x < kChan) {
+                    uint8_t* dst = smem + FrontSmem::c1 + (size_t)(y * kChan + x) * 16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16(fmaxf(a[8 * j + 0] + s_b1[8 * j + 0], 0.f), fmaxf(a[8 * j + 1] + s_b1[8 * j + 1], 0.f));
+                        o.y = pack_bf16(fmaxf(a[8 * j + 2] + s_b1[8 * j + 2], 0.f), fmaxf(a[8 * j + 3] + s_b1[8 * j + 3], 0.f));
+                        o.z = pack_bf16(fmaxf(a[8 * j + 4] + s_b1[8 * j + 4], 0.f), fmaxf(a[8 * j + 5] + s_b1[8 * j + 5], 0.f));
+                        o.w = pack_bf16(fmaxf(a[8 * j + 6] + s_b1[8 * j + 6], 0.f), fmaxf(a[8 * j + 7] + s_b1[8 * j + 7], 0.f));
+                        *reinterpret_cast<uint4*>(dst + (size_t)j * kPlaneC1) = o;
                     }
                 }
             }
-            umma::mma_commit(&bar[1]);
-        }
-        // the input grid and the patch matrix are free since conv1 completed: stage the next frame
-        // while the tensor core works through conv2
-        if (f + (int)gridDim.x < n_frames) stage_input(f + gridDim.x);
-        alive = umma::mbar_wait_bounded(&bar[1], phase);
-        umma::fence_after_sync();
-        if (!alive) break;
-        // ---- epilogue 2: 2x2 max pool (rows: two tiles, columns: lane pairs) + bias + relu -> global ----
-        uint8_t* out = pooled2 + (size_t)f * (4 * kPool2 * 16);
-        const int x = warp * 32 + lane;
-        for (int py = 0; py < 4; ++py) {
-            float a[32], b[32];
-            umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(2 * py) * 32u, a);
-            umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(2 * py + 1) * 32u, b);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float m = fmaxf(a[j], b[j]);
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                a[j] = fmaxf(m + s_b2[j], 0.f);
+            umma::fence_smem_to_async();
+            umma::fence_before_sync();
+            mbar_arrive(&rdy[1]);
+            // the input grid and the patch matrix are free since conv1 completed: stage the next frame
+            // while the tensor core works through conv2
+            const bool more = f + (int)gridDim.x < n_frames;
+            if (more) {
+                stage_input();
+                if (f + 2 * (int)gridDim.x < n_frames) fetch_input(f + 2 * gridDim.x);
             }
-            if ((x & 1) == 0 && x < 126) {
-                uint8_t* dst = out + (size_t)(py * 63 + (x >> 1)) * 16;
+            alive = umma::mbar_wait_bounded(&bar[1], phase);
+            umma::fence_after_sync();
+            if (!alive) break;
+            // ---- epilogue 2: 2x2 max pool (rows: two tiles, columns: lane pairs) + bias + relu -> global ----
+            {
+                uint8_t* out = pooled2 + (size_t)f * (4 * kPool2 * 16);
+                const int x = quarter * 32 + lane, py = group;
+                float a[32], b[32];
+                umma::tmem_ld32(tmem + lane_addr + (uint32_t)(2 * py) * 32u, a);
+                umma::tmem_ld32(tmem + lane_addr + (uint32_t)(2 * py + 1) * 32u, b);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 o;
-                    o.x = pack_bf16(a[8 * j + 0], a[8 * j + 1]);
-                    o.y = pack_bf16(a[8 * j + 2], a[8 * j + 3]);
-                    o.z = pack_bf16(a[8 * j + 4], a[8 * j + 5]);
-                    o.w = pack_bf16(a[8 * j + 6], a[8 * j + 7]);
-                    *reinterpret_cast<uint4*>(dst + (size_t)j * (kPool2 * 16)) = o;
+                for (int j = 0; j < 32; ++j) {
+                    float m = fmaxf(a[j], b[j]);
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    a[j] = fmaxf(m + s_b2[j], 0.f);
+                }
+                if ((x & 1) == 0 && x < 126) {
+                    uint8_t* dst = out + (size_t)(py * 63 + (x >> 1)) * 16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16(a[8 * j + 0], a[8 * j + 1]);
+                        o.y = pack_bf16(a[8 * j + 2], a[8 * j + 3]);
+                        o.z = pack_bf16(a[8 * j + 4], a[8 * j + 5]);
+                        o.w = pack_bf16(a[8 * j + 6], a[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(dst + (size_t)j * (kPool2 * 16)) = o;
+                    }
                 }
             }
+            if (more) {   // next frame: patch matrix staged, accumulators drained
+                umma::fence_before_sync();
+                mbar_arrive(&rdy[0]);
+            }
+            phase ^= 1;
         }
-        phase ^= 1;
+        if (!alive && tid == 0) atomicExch(status, 1);
     }
-    if (!alive && tid == 0) atomicExch(status, 1);
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
@@ -260,19 +323,21 @@ struct MidSmem {
     static constexpr int total = c3 + 8 * kRowsC3 * 16;
 };
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 cnn_mid_kernel(const uint8_t* __restrict__ pooled2, int n_frames, const uint8_t* __restrict__ w3p, const uint8_t* __restrict__ w4p,
                const float* __restrict__ b3, const float* __restrict__ b4, __nv_bfloat16* __restrict__ feat,
                int* __restrict__ status) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar[2];
-    __shared__ __align__(8) uint64_t full[2];
+    __shared__ __align__(8) uint64_t bar[2];    // issuer -> workers: conv3 / conv4 of the current frame have completed
+    __shared__ __align__(8) uint64_t rdy_c3;    // workers -> issuer: conv3 output written (and every older accumulator drained)
+    __shared__ __align__(8) uint64_t full[2];   // bulk copies of a frame's input have landed
     __shared__ uint32_t tmem_slot;
     __shared__ float s_b3[64], s_b4[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    copy_to_smem(smem + MidSmem::w3, w3p, 9 * 4 * 64 * 16, tid, 128);
-    copy_to_smem(smem + MidSmem::w4, w4p, 9 * 8 * 64 * 16, tid, 128);
-    for (int i = tid; i < (MidSmem::total - MidSmem::in3) / 16; i += 128)
+    const int quarter = warp & 3, group = warp >> 2;   // group g handles output channels 16g .. 16g+15
+    copy_to_smem(smem + MidSmem::w3, w3p, 9 * 4 * 64 * 16, tid, kThreads);
+    copy_to_smem(smem + MidSmem::w4, w4p, 9 * 8 * 64 * 16, tid, kThreads);
+    for (int i = tid; i < (MidSmem::total - MidSmem::in3) / 16; i += kThreads)
         reinterpret_cast<uint4*>(smem + MidSmem::in3)[i] = make_uint4(0, 0, 0, 0);   // halo of the `same` conv3, slack rows
     if (tid < 64) {
         s_b3[tid] = b3[tid];
@@ -282,6 +347,7 @@ cnn_mid_kernel(const uint8_t* __restrict__ pooled2, int n_frames, const uint8_t*
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&rdy_c3, kWorkers);
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         mbar_fence_init();
@@ -294,6 +360,7 @@ cnn_mid_kernel(const uint8_t* __restrict__ pooled2, int n_frames, const uint8_t*
     const uint32_t s_base = smem_u32(smem);
     constexpr uint32_t kPlaneIn3 = kRowsIn3 * 16, kPlaneC3 = kRowsC3 * 16;
     const uint32_t idesc64 = umma::instr_desc_bf16(128, 64);
+    bool alive = true;
 
     // interior rows of one frame's pooled conv2 output -> padded grid in buffer b (16 bulk copies of 63 pixels)
     auto fetch = [&](int f, int b) {
@@ -306,133 +373,144 @@ cnn_mid_kernel(const uint8_t* __restrict__ pooled2, int n_frames, const uint8_t*
                             src + (size_t)pl * (kPool2 * 16) + (size_t)y * 63 * 16, 63 * 16, &full[b]);
     };
 
-    uint32_t phase = 0, full_phase[2] = {0, 0};
-    bool alive = true;
-    int it = 0;
-    if (tid == 0 && (int)blockIdx.x < n_frames) fetch(blockIdx.x, 0);
-    for (int f = blockIdx.x; f < n_frames && alive; f += gridDim.x, ++it) {
-        const int b = it & 1;
-        const uint32_t in_base = s_base + MidSmem::in3 + (uint32_t)b * MidSmem::in3_bytes;
-        if (tid == 0 && f + (int)gridDim.x < n_frames) fetch(f + gridDim.x, b ^ 1);
-        alive = umma::mbar_wait_bounded(&full[b], full_phase[b]);
-        full_phase[b] ^= 1;
-        if (!alive) break;
-        // ---- conv3: 3 tiles x 9 taps x 2 x (M128, N64, K16) ----
-        if (tid == 0) {
+    if (warp == kWorkers / 32) {
+        // ================================ issuer warp ================================
+        // Program order on the tensor pipe makes most hazards vanish: conv3 of frame f+1 is issued behind conv4
+        // of frame f, whose issue waited for the epilogue that drained conv3(f)'s columns; conv4(f+1) waits for
+        // rdy_c3(f+1), which the workers signal after they are done with everything of frame f.
+        const uint64_t dw3 = umma::smem_desc(s_base + MidSmem::w3, 1024, 128);
+        const uint64_t dw4 = umma::smem_desc(s_base + MidSmem::w4, 1024, 128);
+        const uint64_t dc3 = umma::smem_desc(s_base + MidSmem::c3, kPlaneC3, 128);
+        uint32_t phase = 0, full_phase0 = 0, full_phase1 = 0;
+        int it = 0;
+        for (int f = blockIdx.x; f < n_frames && alive; f += gridDim.x, ++it) {
+            const int b = it & 1;
+            alive = umma::mbar_wait_bounded(&full[b], b ? full_phase1 : full_phase0);
+            if (b) full_phase1 ^= 1; else full_phase0 ^= 1;
             umma::fence_after_sync();
-            for (int t = 0; t < kTiles3; ++t) {
-                bool acc = false;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t shift = (uint32_t)(t * 128 + (tap / 3) * kW3 + (tap % 3));
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const uint64_t da = umma::smem_desc(in_base + (uint32_t)(2 * kk) * kPlaneIn3 + shift * 16u, kPlaneIn3, 128);
-                        const uint64_t db = umma::smem_desc(s_base + MidSmem::w3 + (uint32_t)tap * 4096u + (uint32_t)(2 * kk) * 1024u,
-                                                            1024, 128);
-                        umma::mma_bf16(tmem + (uint32_t)t * 64u, da, db, idesc64, acc);
-                        acc = true;
+            if (!alive) break;
+            if (umma::elect_one()) {
+                const uint64_t din = umma::smem_desc(s_base + MidSmem::in3 + (uint32_t)b * MidSmem::in3_bytes, kPlaneIn3, 128);
+#pragma unroll 1
+                for (int t = 0; t < kTiles3; ++t) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t shift = (uint32_t)(t * 128 + (tap / 3) * kW3 + (tap % 3));
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
+                            umma::mma_bf16(tmem + (uint32_t)t * 64u, din + (uint64_t)(shift + (uint32_t)(2 * kk) * (kPlaneIn3 / 16)),
+                                           dw3 + (uint64_t)((tap * 4096 + 2 * kk * 1024) / 16), idesc64, tap > 0 || kk > 0);
                     }
                 }
+                umma::mma_commit(&bar[0]);
             }
-            umma::mma_commit(&bar[0]);
+            __syncwarp();
+            alive = umma::mbar_wait_bounded(&rdy_c3, phase);
+            umma::fence_after_sync();
+            if (!alive) break;
+            if (umma::elect_one()) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t shift = (uint32_t)((tap / 3) * 63 + (tap % 3));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma::mma_bf16(tmem + 192u, dc3 + (uint64_t)(shift + (uint32_t)(2 * kk) * (kPlaneC3 / 16)),
+                                       dw4 + (uint64_t)((tap * 8192 + 2 * kk * 1024) / 16), idesc64, tap > 0 || kk > 0);
+                }
+                umma::mma_commit(&bar[1]);
+            }
+            __syncwarp();
+            phase ^= 1;
         }
-        alive = umma::mbar_wait_bounded(&bar[0], phase);
-        umma::fence_after_sync();
-        if (!alive) break;
-        // ---- epilogue 3: bias + relu -> bf16 planes, rows re-strided from 65 to 63 ----
-        for (int t = 0; t < kTiles3; ++t) {
-            const int q = t * 128 + warp * 32 + lane;
-            const int y = q / kW3, x = q - y * kW3;
-            const bool valid = y < 4 && x < 63;
-            uint8_t* dst = smem + MidSmem::c3 + (size_t)(y * 63 + x) * 16;
+        if (!alive && lane == 0) atomicExch(status, 2);
+    } else {
+        // ================================ worker warps ================================
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t phase = 0;
+        int it = 0;
+        if (tid == 0) {
+            if ((int)blockIdx.x < n_frames) fetch(blockIdx.x, 0);
+            if ((int)(blockIdx.x + gridDim.x) < n_frames) fetch(blockIdx.x + gridDim.x, 1);
+        }
+        for (int f = blockIdx.x; f < n_frames && alive; f += gridDim.x, ++it) {
+            const int b = it & 1;
+            alive = umma::mbar_wait_bounded(&bar[0], phase);
+            umma::fence_after_sync();
+            if (!alive) break;
+            // ---- epilogue 3: bias + relu -> bf16 planes, rows re-strided from 65 to 63; group g: channels 16g.. ----
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float v[32];
-                umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * 64u + (uint32_t)h * 32u, v);
-                if (valid) {
+            for (int t = 0; t < kTiles3; ++t) {
+                const int q = t * 128 + quarter * 32 + lane;
+                const int y = q / kW3, x = q - y * kW3;
+                float v[16];
+                umma::tmem_ld16(tmem + lane_addr + (uint32_t)t * 64u + (uint32_t)group * 16u, v);
+                if (y < 4 && x < 63) {
+                    uint8_t* dst = smem + MidSmem::c3 + (size_t)(y * 63 + x) * 16 + (size_t)(2 * group) * kPlaneC3;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = h * 32 + 8 * j;
+                    for (int j = 0; j < 2; ++j) {
+                        const int c = group * 16 + 8 * j;
                         uint4 o;
                         o.x = pack_bf16(fmaxf(v[8 * j + 0] + s_b3[c + 0], 0.f), fmaxf(v[8 * j + 1] + s_b3[c + 1], 0.f));
                         o.y = pack_bf16(fmaxf(v[8 * j + 2] + s_b3[c + 2], 0.f), fmaxf(v[8 * j + 3] + s_b3[c + 3], 0.f));
                         o.z = pack_bf16(fmaxf(v[8 * j + 4] + s_b3[c + 4], 0.f), fmaxf(v[8 * j + 5] + s_b3[c + 5], 0.f));
                         o.w = pack_bf16(fmaxf(v[8 * j + 6] + s_b3[c + 6], 0.f), fmaxf(v[8 * j + 7] + s_b3[c + 7], 0.f));
-                        *reinterpret_cast<uint4*>(dst + (size_t)(h * 4 + j) * kPlaneC3) = o;
+                        *reinterpret_cast<uint4*>(dst + (size_t)j * kPlaneC3) = o;
                     }
                 }
             }
-        }
-        umma::fence_smem_to_async();
-        umma::fence_before_sync();
-        __syncthreads();
-        // ---- conv4: 9 taps x 4 x (M128, N64, K16) on rows p = y*63 + x ----
-        if (tid == 0) {
+            umma::fence_smem_to_async();
+            umma::fence_before_sync();
+            mbar_arrive(&rdy_c3);
+            alive = umma::mbar_wait_bounded(&bar[1], phase);
             umma::fence_after_sync();
-            bool acc = false;
-            for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t shift = (uint32_t)((tap / 3) * 63 + (tap % 3));
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t da = umma::smem_desc(s_base + MidSmem::c3 + (uint32_t)(2 * kk) * kPlaneC3 + shift * 16u, kPlaneC3, 128);
-                    const uint64_t db = umma::smem_desc(s_base + MidSmem::w4 + (uint32_t)tap * 8192u + (uint32_t)(2 * kk) * 1024u,
-                                                        1024, 128);
-                    umma::mma_bf16(tmem + 192u, da, db, idesc64, acc);
-                    acc = true;
-                }
-            }
-            umma::mma_commit(&bar[1]);
-        }
-        alive = umma::mbar_wait_bounded(&bar[1], phase);
-        umma::fence_after_sync();
-        if (!alive) break;
-        // ---- epilogue 4: bias + relu -> staging [p][64] bf16 (over this frame's input buffer, now dead) ----
-        uint8_t* stage = smem + MidSmem::in3 + (size_t)b * MidSmem::in3_bytes;   // 128 rows x 128 bytes
-        {
-            const int p = warp * 32 + lane;
+            if (!alive) break;
+            // ---- epilogue 4: bias + relu -> staging [p][64] bf16 (over this frame's input buffer, now dead) ----
+            uint8_t* stage = smem + MidSmem::in3 + (size_t)b * MidSmem::in3_bytes;   // 128 rows x 128 bytes
+            {
+                const int p = quarter * 32 + lane;
+                float v[16];
+                umma::tmem_ld16(tmem + lane_addr + 192u + (uint32_t)group * 16u, v);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float v[32];
-                umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 192u + (uint32_t)h * 32u, v);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = h * 32 + 8 * j;
+                for (int j = 0; j < 2; ++j) {
+                    const int c = group * 16 + 8 * j;
                     uint4 o;
                     o.x = pack_bf16(fmaxf(v[8 * j + 0] + s_b4[c + 0], 0.f), fmaxf(v[8 * j + 1] + s_b4[c + 1], 0.f));
                     o.y = pack_bf16(fmaxf(v[8 * j + 2] + s_b4[c + 2], 0.f), fmaxf(v[8 * j + 3] + s_b4[c + 3], 0.f));
                     o.z = pack_bf16(fmaxf(v[8 * j + 4] + s_b4[c + 4], 0.f), fmaxf(v[8 * j + 5] + s_b4[c + 5], 0.f));
                     o.w = pack_bf16(fmaxf(v[8 * j + 6] + s_b4[c + 6], 0.f), fmaxf(v[8 * j + 7] + s_b4[c + 7], 0.f));
                     // 16-byte chunks of a row are rotated by the row index: conflict-free column reads below
-                    *reinterpret_cast<uint4*>(stage + (size_t)p * 128 + (size_t)(((h * 4 + j) + p) & 7) * 16) = o;
+                    *reinterpret_cast<uint4*>(stage + (size_t)p * 128 + (size_t)(((2 * group + j) + p) & 7) * 16) = o;
                 }
             }
+            worker_sync();
+            // ---- 2x2 max pool over (y, x) in {0,1} x {2px, 2px+1} -> 30 x 64 features (Keras flatten order x*64 + c) ----
+            if (tid < 30 * 8) {
+                const int px = tid >> 3, g = tid & 7;
+                __nv_bfloat162 m[4];
+                bool first = true;
+#pragma unroll
+                for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+                    for (int xx = 0; xx < 2; ++xx) {
+                        const int p = yy * 63 + 2 * px + xx;
+                        const uint4 r = *reinterpret_cast<const uint4*>(stage + (size_t)p * 128 + (size_t)((g + p) & 7) * 16);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) m[k] = first ? h2[k] : __hmax2(m[k], h2[k]);
+                        first = false;
+                    }
+                *reinterpret_cast<uint4*>(feat + (size_t)f * kFeat + (size_t)px * 64 + (size_t)g * 8) = *reinterpret_cast<uint4*>(m);
+            }
+            worker_sync();
+            // restore the zero halo the staging rows overwrote and hand the buffer back to the bulk-copy engine
+            for (int i = tid; i < 128 * 8; i += kWorkers) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0, 0, 0, 0);
+            umma::fence_smem_to_async();
+            worker_sync();
+            if (tid == 0 && f + 2 * (int)gridDim.x < n_frames) fetch(f + 2 * gridDim.x, b);
+            phase ^= 1;
         }
-        __syncthreads();
-        // ---- 2x2 max pool over (y, x) in {0,1} x {2px, 2px+1} -> 30 x 64 features (Keras flatten order x*64 + c) ----
-        for (int i = tid; i < 30 * 8; i += 128) {
-            const int px = i >> 3, g = i & 7;
-            __nv_bfloat162 m[4];
-            bool first = true;
-#pragma unroll
-            for (int yy = 0; yy < 2; ++yy)
-#pragma unroll
-                for (int xx = 0; xx < 2; ++xx) {
-                    const int p = yy * 63 + 2 * px + xx;
-                    const uint4 r = *reinterpret_cast<const uint4*>(stage + (size_t)p * 128 + (size_t)((g + p) & 7) * 16);
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) m[k] = first ? h2[k] : __hmax2(m[k], h2[k]);
-                    first = false;
-                }
-            *reinterpret_cast<uint4*>(feat + (size_t)f * kFeat + (size_t)px * 64 + (size_t)g * 8) = *reinterpret_cast<uint4*>(m);
-        }
-        // restore the zero halo the staging rows overwrote (rows 0..127 of plane 0 span the halo of the grid),
-        // and hand the buffer back to the bulk-copy engine
-        for (int i = tid; i < 128 * 8; i += 128) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0, 0, 0, 0);
-        umma::fence_smem_to_async();
-        umma::fence_before_sync();
-        __syncthreads();
-        phase ^= 1;
+        if (!alive && tid == 0) atomicExch(status, 2);
     }
-    if (!alive && tid == 0) atomicExch(status, 2);
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 256);
@@ -597,9 +675,9 @@ cudaError_t launch_cnn_forward(const CnnWeights& w, const float* env_t, int step
     for (long long f0 = 0; f0 < n_frames; f0 += chunk_frames) {
         const int nf = (int)std::min<long long>(chunk_frames, n_frames - f0);
         const int grid = std::min(nf, sm_count);
-        cnn_front_kernel<<<grid, 128, FrontSmem::total, stream>>>(env_t, step, frame0 + f0, nf, w.w1, w.w2, w.b1, w.b2, pooled2,
+        cnn_front_kernel<<<grid, kThreads, FrontSmem::total, stream>>>(env_t, step, frame0 + f0, nf, w.w1, w.w2, w.b1, w.b2, pooled2,
                                                                   bad_flag, status);
-        cnn_mid_kernel<<<grid, 128, MidSmem::total, stream>>>(pooled2, nf, w.w3, w.w4, w.b3, w.b4, feat, status);
+        cnn_mid_kernel<<<grid, kThreads, MidSmem::total, stream>>>(pooled2, nf, w.w3, w.w4, w.b3, w.b4, feat, status);
         cnn_dense_kernel<<<(nf + 127) / 128, 128, DenseSmem::total, stream>>>(feat, nf, w.w5, w.b5, w.w6, w.b6, scores + (size_t)f0 * 2,
                                                                               status);
         cudaError_t e = cudaGetLastError();

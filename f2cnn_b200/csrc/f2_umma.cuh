@@ -57,6 +57,19 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // (tcgen05.mma reads its operands through it)
 __device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a fully active warp (elect.sync): the tensor-core instructions are issued from warp-uniform
+// code by the elected lane, which lets the compiler keep descriptors in uniform registers and emit the
+// UTCHMMA without a per-thread election loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA: D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread ---------------------------------------
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          bool accumulate) {
