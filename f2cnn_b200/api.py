@@ -338,6 +338,75 @@ def dense_frames(wave, coefs, LPF=False, CUTOFF=100, radius=5, step=160, normali
     return host
 
 
+def evaluate_front_end(wave, coefs, LPF=False, CUTOFF=100, radius=5, step=160, frames=True, dtype=np.float64):
+    """ONE filterbank pass for `cnn eval*` (Evaluating.py:52-80): the (C, n) envelopes the figure shows
+    and the (nb, 2R+1, C) normalised frames model.predict takes, both from the same time-major envelope.
+    frames=False returns (envelopes, device env_t) for a consumer on the device (api.cnn_evaluate)."""
+    w = _as_wave(wave)
+    coefs = np.asarray(coefs, dtype=np.float64)
+    plan = engine.plan_for(coefs)
+    n = int(w.shape[0])
+    dots = 2 * radius + 1
+    if n == 0:
+        raise ValueError("N must be positive.")
+    batch = plan.batch([n], step=step)
+    res = batch.run(_to_device(w, plan.device), lpf=LPF, cutoff=CUTOFF, env=torch.float64, env_t=True)
+    envelopes = _to_host(res["env"]).reshape(plan.n_channels, n)
+    if not frames:
+        return envelopes, res["env_t"]
+    nb = int(n - dots * step)
+    if nb <= 0:
+        return envelopes, np.zeros((0, dots, plan.n_channels), dtype=dtype)
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    out, flag = engine.dense_frames(res["env_t"], dots, step, 0, nb, normalize=True, out_dtype=tdt)
+    host = _to_host(out)
+    if int(flag.item()) != 0:
+        raise ValueError("values must all be positive")  # Training.py:18-20
+    return envelopes, host
+
+
+_networks = OrderedDict()
+
+
+def _network_for(weights):
+    """Tensor-core network for a list of Keras-layout arrays (or an F2CNN module), cached by content."""
+    from . import cnn
+    arrays = cnn.keras_arrays(weights) if isinstance(weights, torch.nn.Module) else [np.asarray(a) for a in weights]
+    h = hashlib.sha1()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a, dtype=np.float32).tobytes())
+    key = (h.hexdigest(), torch.cuda.current_device())
+    net = _networks.get(key)
+    if net is None:
+        net = cnn.TensorCoreCNN(arrays)
+        _networks[key] = net
+        while len(_networks) > 4:
+            _networks.popitem(last=False)
+    return net
+
+
+def cnn_evaluate(wave, coefs, weights, LPF=False, CUTOFF=100, radius=5, step=160, with_envelopes=True):
+    """`cnn eval*` from waveform to scores on the device (Evaluating.py:52-87): filterbank -> envelope ->
+    every stride-1 frame normalised and run through the reference network on the tensor cores
+    (csrc/f2_cnn.cu), without materialising the (nb, 11, 128) frame tensor.  weights: the 12 arrays of
+    Keras' model.get_weights() or an f2cnn_b200.cnn.F2CNN module.  Returns (scores (nb, 2) float32,
+    envelopes (C, n) float64 or None).  Only the configured geometry (RADIUS = 5, 128 channels)."""
+    coefs = np.asarray(coefs, dtype=np.float64)
+    if radius != 5 or coefs.shape[0] != 128:
+        raise ValueError("the tensor-core network is built for RADIUS = 5 and 128 channels")
+    net = _network_for(weights)
+    if with_envelopes:
+        envelopes, env_t = evaluate_front_end(wave, coefs, LPF, CUTOFF, radius, step, frames=False)
+    else:
+        w = _as_wave(wave)
+        plan = engine.plan_for(coefs)
+        envelopes = None
+        env_t = plan.batch([int(w.shape[0])], step=step).run(_to_device(w, plan.device), lpf=LPF, cutoff=CUTOFF,
+                                                             env_t=True)["env_t"]
+    scores = net.predict_envelope(env_t, step)
+    return _to_host(scores), envelopes
+
+
 def label_fit(tracks, firsts, centers, radius=5, step=160):
     """Slope labels for a whole corpus in one launch (LabelDataGenerator.py:60-68).
 

@@ -180,3 +180,24 @@ def keras_arrays(model):
         out.append(lin.weight.detach().float().t().contiguous().cpu().numpy())
         out.append(lin.bias.detach().float().cpu().numpy())
     return out
+
+
+WEIGHT_NAMES = ("conv1_kernel", "conv1_bias", "conv2_kernel", "conv2_bias", "conv3_kernel", "conv3_bias",
+                "conv4_kernel", "conv4_bias", "dense1_kernel", "dense1_bias", "dense2_kernel", "dense2_bias")
+
+
+def save_weights(path, source):
+    """Write the 12 parameter arrays (Keras get_weights() order and layout) as an .npz: what
+    scripts.CNN.Evaluating takes as `model` where no Keras is installed."""
+    arrays = keras_arrays(source) if isinstance(source, torch.nn.Module) else list(source)
+    np.savez(path, **{n: np.asarray(a, dtype=np.float32) for n, a in zip(WEIGHT_NAMES, arrays)})
+
+
+def load_weights(path):
+    """The 12 arrays of an .npz written by save_weights (or by numpy.savez(path, *model.get_weights()))."""
+    with np.load(path, allow_pickle=False) as z:
+        if all(n in z.files for n in WEIGHT_NAMES):
+            return [z[n] for n in WEIGHT_NAMES]
+        if all("arr_%d" % i in z.files for i in range(12)):
+            return [z["arr_%d" % i] for i in range(12)]
+    raise ValueError("%s does not hold the 12 parameter arrays of the reference network" % path)

@@ -2,10 +2,14 @@
 
 What the reference does per utterance (EvaluateOneWavArray, reference :27-113): filterbank and
 envelope, then 25 s of pure-Python dense framing (:70-78), ~1 s of per-frame normalizeInput
-(:79-80), then Keras prediction, an accuracy heuristic and a matplotlib figure.  Here the first
-three are one GPU launch sequence (api.dense_frames, 0.7 ms of device time for a 3 s
-utterance); prediction and plotting still belong to the reference tree and to Keras and are
-imported lazily, exactly where the reference needs them.
+(:79-80), then Keras prediction, an accuracy heuristic and a matplotlib figure.  Here everything
+up to the scores is ONE filterbank pass on the GPU: the time-major envelope feeds the
+reference network on the tensor cores (api.cnn_evaluate -> csrc/f2_cnn.cu, 3.4 ms for the
+46 240 frames of a 3 s utterance) and, transposed, is the matrix the figure shows.  `model` may
+be an .npz of the 12 arrays of model.get_weights() (cnn.save_weights) -- no Keras needed -- or
+a Keras model, whose weights are then read with get_weights(); a geometry other than the
+configured RADIUS = 5 / 128 channels keeps Keras' own predict on the GPU-made frames.  The figure
+still belongs to the reference tree (matplotlib) and is imported where the reference needs it.
 
 Public names, signatures, defaults and side effects (files written under OutputWavFiles/,
 graphs/) follow the reference; the bodies are organised around small helpers.
@@ -107,6 +111,23 @@ def _label_accuracy(labels, decisions, step):
     return hits / counted
 
 
+def _resolve_model(model, st):
+    """(weights, keras network): the 12 parameter arrays for the tensor-core kernels when the geometry is
+    the configured one, else the Keras network whose predict takes the frames (reference :84-86)."""
+    from ... import cnn
+    tensor_core = st.dots == 11 and st.nchannels == 128
+    for cand in (model, str(model) + '.npz'):
+        if str(cand).endswith('.npz') and os.path.isfile(cand):
+            if not tensor_core:
+                raise ValueError("an .npz model needs the configured geometry (RADIUS = 5, 128 channels)")
+            return cnn.load_weights(cand), None
+    import keras  # absent here: the reference's own ImportError
+    network = keras.models.load_model(model)
+    if tensor_core and hasattr(network, 'get_weights'):
+        return network.get_weights(), network
+    return None, network
+
+
 def EvaluateOneWavArray(wavArray, framerate, wavFileName, model='last_trained_model', LPF=False, CUTOFF=100,
                         CENTER_FREQUENCIES=None, FILTERBANK_COEFFICIENTS=None):
     """One waveform through front end, CNN and figure (reference :27-113)."""
@@ -121,9 +142,10 @@ def EvaluateOneWavArray(wavArray, framerate, wavFileName, model='last_trained_mo
     found = ExtractLabel(wavFileName, cfg)
     labels = None if found is None else [(row[-4], row[-1]) for row in found]
 
-    frames, centre, coefs, step = PrepareInputFromArray(wavArray, framerate, cfg, LPF, CUTOFF, CENTER_FREQUENCIES,
-                                                        FILTERBANK_COEFFICIENTS)
-    envelopes = api.filterbank_envelope(wavArray, coefs, LPF, CUTOFF)  # the figure shows them at full rate
+    step = int(framerate * cfg.getint('CNN', 'SAMPLING_PERIOD') * 1e-6)
+    centre, coefs = _bank(framerate, st, CENTER_FREQUENCIES, FILTERBANK_COEFFICIENTS)
+    print("Applying filterbank...")
+    print("Extraction Envelope with {}Hz Low Pass Filter...".format(CUTOFF) if LPF else "Extracting Envelope...")
 
     stem = os.path.splitext(wavFileName)[0]
     print("Extracting Formants...")
@@ -131,12 +153,22 @@ def EvaluateOneWavArray(wavArray, framerate, wavFileName, model='last_trained_mo
     print("Extracting Phonemes...")
     phonemes = ExtractPhonemes(stem + '.PHN')
 
+    print("Generating input data for CNN...")
+    weights, network = _resolve_model(model, st)
     print("Evaluating the data with the pretrained model...")
-    import keras
-    network = keras.models.load_model(model)
-    scores = network.predict(frames.reshape(frames.shape[0], st.dots, st.nchannels, 1), verbose=1)
-    keras.backend.clear_session()
-    del network, frames
+    if weights is not None:
+        # waveform -> scores on the device; the envelopes come out of the same pass
+        scores, envelopes = api.cnn_evaluate(wavArray, coefs, weights, LPF, CUTOFF, st.radius, step)
+        print("INPUT SHAPE:", (scores.shape[0], st.dots, st.nchannels))
+    else:
+        envelopes, frames = api.evaluate_front_end(wavArray, coefs, LPF, CUTOFF, st.radius, step)
+        print("INPUT SHAPE:", frames.shape)
+        scores = network.predict(frames.reshape(frames.shape[0], st.dots, st.nchannels, 1), verbose=1)
+        del frames
+    if network is not None:
+        import keras
+        keras.backend.clear_session()
+        del network
 
     accuracy = _label_accuracy(labels, _decisions(scores), step) if labels is not None else None
     print("Plotting...")
