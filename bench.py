@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances of the corpus (default: the config's 4620)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the side configs (single utterance, 600 s stream, evalnoise)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-for-bit check against the 1-GPU result")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -162,6 +163,79 @@ def cpu_arm(coefs, lengths, seed, seconds, steps=1, warmup=0):
                       "reference algorithm, OpenMP over channels, in memory" % (per_step, total_n // max(steps, 1),
                                                                                 steps),
             "seconds": total_t}, total_t / max(steps, 1)
+
+
+def other_configs(coefs128):
+    """The BASELINE.json configs that are not the headline, timed on the device (rank 0, N = 1):
+    configs[0] one 3 s utterance (latency of the public call), configs[3] the 600 s x 256-channel stream
+    at 20/50/100 Hz cut-off, configs[4] evalnoise -- noisy float64 utterances through filterbank,
+    envelope and the tensor-core CNN on every stride-1 frame."""
+    import torch
+    from f2cnn_b200 import api, cnn, engine, synth
+    from f2cnn_b200.gammatone import filters
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = engine.DeviceEvent(), engine.DeviceEvent()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_ms(b) / reps
+
+    out = {}
+    fma_peak = 148 * 128 * 2 * 1965e6
+    # ---- configs[0]: single utterance, host wave in -> host windows out ----
+    w = synth.white_noise_i16(48000, 0)
+    centers = synth.label_grid(48000)
+    api.features_to_windows([w], coefs128, [centers], True, CUTOFF)
+    t = time.perf_counter()
+    for _ in range(20):
+        api.features_to_windows([w], coefs128, [centers], True, CUTOFF)
+    ms = (time.perf_counter() - t) / 20 * 1e3
+    out["config1_single_utterance"] = {"host_ms_per_call": ms, "channel_samples_per_s": C * 48000 / ms * 1e3,
+                                       "path": "api.features_to_windows, 3 s x 128 ch, time-chunked"}
+    # ---- configs[3]: 600 s stream, 256 channels ----
+    n = 9_600_000
+    co256 = filters.make_erb_filters(FS, filters.centre_freqs(FS, 256, LOW))
+    plan4 = engine.plan_for(co256)
+    w4 = torch.from_numpy(synth.white_noise_i16(n, seed=2)).cuda()
+    b4 = plan4.batch([n])
+    dec4 = torch.empty((b4.total_frames, 256), dtype=torch.float32, device="cuda")
+    for cut in (20, 50, 100):
+        ms = timed(lambda: b4.run(w4, lpf=True, cutoff=cut, out={"dec": dec4}), reps=3, warm=1)
+        rate = 256.0 * n / ms * 1e3
+        out["config4_stream_600s_256ch_cutoff%d" % cut] = {"device_ms": ms, "channel_samples_per_s": rate, "items": b4.num_items,
+                                                           "fma_roofline_frac": FLOP_PER_CS * rate / fma_peak}
+    del w4, dec4, b4
+    # ---- configs[4]: evalnoise ----
+    model = cnn.seeded_model(0)
+    net = cnn.TensorCoreCNN(model)
+    plan = engine.plan_for(coefs128)
+    base = synth.speech_like_i16(48000, seed=31).astype(np.float64)
+    rms = float(np.sqrt(np.mean(base ** 2)))
+    for snr_db in (0, 10, 20):
+        noisy = base + np.random.default_rng(3 + snr_db).normal(scale=rms / 10 ** (snr_db / 20.0), size=48000)
+        wd = torch.from_numpy(noisy).cuda()
+        b5 = plan.batch([48000])
+
+        def run():
+            env_t = b5.run(wd, lpf=True, cutoff=CUTOFF, env_t=True)["env_t"]
+            return env_t, net.predict_envelope(env_t, STEP)
+
+        ms_all = timed(run, reps=5)
+        env_t, scores = run()
+        ms_cnn = timed(lambda: net.predict_envelope(env_t, STEP), reps=5)
+        frames = 48000 - 11 * STEP
+        out["config5_evalnoise_snr%ddB" % snr_db] = {
+            "frames": frames, "device_ms_filterbank_envelope_cnn": ms_all, "device_ms_cnn": ms_cnn,
+            "frames_per_s": frames / ms_all * 1e3, "cnn_tflops": frames * 2 * 21.0e6 / ms_cnn / 1e9,
+            "rising_fraction": float((scores[:, 1] > scores[:, 0]).float().mean()),
+            "cnn": "tcgen05 kernels (csrc/f2_cnn.cu), bf16 x bf16 -> fp32, seeded weights (no trained model ships with the reference)"}
+    return out
 
 
 def main():
@@ -400,11 +474,19 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:
         cpu, _ = cpu_arm(coefs, lengths, 1, args.cpu_seconds)
+    others = None
+    if world == 1 and not args.no_configs:
+        del wave_dev, wave_host
+        torch.cuda.empty_cache()
+        try:
+            others = other_configs(coefs)
+        except Exception as e:  # the headline line must not depend on the side configs
+            others = {"error": repr(e)}
     out = {"metric": "channel-samples/sec (filterbank+envelope)", "value": value, "unit": "channel-samples/s",
            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps,
-           "roofline": roofline, "cpu_baseline": cpu, "windows_per_step": n_windows_all}
+           "roofline": roofline, "cpu_baseline": cpu, "windows_per_step": n_windows_all, "other_configs": others}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

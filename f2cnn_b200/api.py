@@ -98,6 +98,126 @@ def extract_envelope_from_matrix(matrix, LPF=False, CUTOFF=100, dtype=np.float64
     return _to_host(out)
 
 
+class MatrixStream:
+    """Full-rate (C, n) matrices for MANY utterances -- what the file drivers `prepare filter` and `prepare
+    envelope` write (GammatoneFiltering.py:69-83, EnvelopeExtraction.py:101-117) -- without paying the
+    per-call set-up of the array functions: utterances are processed in batches that fill one of two
+    pinned host slots; the matrices handed back are VIEWS into the slot, so writer threads save them
+    without another copy while the next batch is computed into the other slot.  A slot is recycled when
+    the futures registered with retire() for it have finished.
+
+    mode "filterbank": waves -> erb_filterbank (+ envelope with with_env): process(list of waves).
+    mode "envelope":   loaded .GFB matrices -> ExtractEnvelopeFromMatrix: process(list of (C, n) arrays)."""
+
+    def __init__(self, coefs, mode="filterbank", LPF=False, CUTOFF=100, with_env=False, dtype=np.float64,
+                 slot_bytes=768 << 20):
+        # the envelope of a loaded matrix does not depend on a filterbank: any plan of the device will do
+        self.plan = engine.any_plan() if coefs is None else engine.plan_for(np.asarray(coefs, dtype=np.float64))
+        self.mode, self.lpf, self.cutoff, self.with_env = mode, bool(LPF), CUTOFF, bool(with_env)
+        self.dtype = np.dtype(dtype)
+        self.tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        self.slot_bytes = int(slot_bytes)
+        self._slots = [torch.empty(self.slot_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        self._guards = [[], []]
+        self._dev = torch.empty(self.slot_bytes, dtype=torch.uint8, device=self.plan.device)
+        self._stage = None
+        self._k = 0
+        self.per_value = self.dtype.itemsize * (2 if (mode == "filterbank" and with_env) else 1)
+
+    def batches(self, sizes):
+        """Split a list of matrix sizes (elements: C * n per utterance) into runs that fit a slot."""
+        out, cur, used = [], [], 0
+        for i, sz in enumerate(sizes):
+            need = int(sz) * self.per_value
+            if need > self.slot_bytes:
+                raise ValueError("one matrix of %d bytes does not fit a slot of %d" % (need, self.slot_bytes))
+            if used + need > self.slot_bytes and cur:
+                out.append(cur)
+                cur, used = [], 0
+            cur.append(i)
+            used += need
+        if cur:
+            out.append(cur)
+        return out
+
+    def retire(self, futures):
+        """Futures (writer jobs) that still read the views returned by the last process() call."""
+        self._guards[self._k ^ 1] = list(futures)
+
+    def _pinned_stage(self, nbytes):
+        if self._stage is None or self._stage.numel() < nbytes:
+            self._stage = torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True)
+        return self._stage
+
+    def process(self, items):
+        k = self._k
+        for fut in self._guards[k]:
+            fut.result()
+        self._guards[k] = []
+        C = self.plan.n_channels
+        slot, dev = self._slots[k], self._dev
+        stream = torch.cuda.current_stream(self.plan.device)
+        views = []
+        if self.mode == "filterbank":
+            waves = [_as_wave(w) for w in items]
+            if len({w.dtype for w in waves}) > 1:
+                waves = [w.astype(np.float64) for w in waves]
+            lengths = np.asarray([w.shape[0] for w in waves], dtype=np.int64)
+            total = int(lengths.sum())
+            if total == 0:
+                z = np.zeros((C, 0), dtype=self.dtype)
+                return [(z, z.copy()) if self.with_env else z for _ in waves]
+            wdt = torch.from_numpy(waves[0][:0]).dtype
+            stage = self._pinned_stage(total * waves[0].dtype.itemsize).view(wdt)[:total]
+            np.concatenate(waves, out=stage.numpy())
+            wave_dev = stage.to(self.plan.device, non_blocking=True)
+            nval = C * total
+            out = {"gfb": dev[:nval * self.dtype.itemsize].view(self.tdt)}
+            if self.with_env:
+                out["env"] = dev[nval * self.dtype.itemsize:2 * nval * self.dtype.itemsize].view(self.tdt)
+            self.plan.batch(lengths).run(wave_dev, lpf=self.lpf, cutoff=self.cutoff, out=out, gfb=self.tdt,
+                                         env=self.tdt if self.with_env else None)
+            nbytes = nval * self.per_value
+            slot[:nbytes].copy_(dev[:nbytes], non_blocking=True)
+            stream.synchronize()
+            host = slot.numpy()
+            off = 0
+            for n in lengths:
+                sz = C * int(n) * self.dtype.itemsize
+                g = host[off:off + sz].view(self.dtype).reshape(C, int(n))
+                if self.with_env:
+                    e0 = nval * self.dtype.itemsize + off
+                    views.append((g, host[e0:e0 + sz].view(self.dtype).reshape(C, int(n))))
+                else:
+                    views.append(g)
+                off += sz
+        else:
+            off = 0
+            placed = []
+            for m in items:
+                m = np.asarray(m)
+                if m.ndim != 2:
+                    raise ValueError("matrix must be two-dimensional (channels x samples)")
+                if m.dtype not in (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int16)):
+                    m = m.astype(np.float64)
+                rows, n = m.shape
+                if n == 0:
+                    raise ValueError("N must be positive.")
+                src = self._pinned_stage(m.nbytes)[:m.nbytes]
+                np.copyto(src.numpy().view(m.dtype).reshape(m.shape), m)
+                m_dev = src.to(self.plan.device, non_blocking=True).view(torch.from_numpy(m[:0, :0]).dtype).view(rows, n)
+                res = self.plan.envelope_rows(m_dev, self.lpf, self.cutoff, out_dtype=self.tdt)
+                sz = rows * n * self.dtype.itemsize
+                slot[off:off + sz].copy_(res.view(-1).view(torch.uint8), non_blocking=True)
+                stream.synchronize()   # the staging buffer is reused by the next matrix
+                placed.append((off, sz, rows, n))
+                off += sz
+            host = slot.numpy()
+            views = [host[o:o + sz].view(self.dtype).reshape(r, n) for o, sz, r, n in placed]
+        self._k ^= 1
+        return views
+
+
 def _rows_op(matrix, op, lpf, cutoff):
     m = np.asarray(matrix)
     if m.dtype not in (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int16)):

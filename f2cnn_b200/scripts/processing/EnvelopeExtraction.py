@@ -89,25 +89,40 @@ def ExtractAllEnvelopes(LPF=False, CUTOFF=100):
     print(len(found), ".GFB.npy files found")
 
     InitProcesses(Value('i', 0))
-    # one thread drives the GPU; matrix loads run a few files ahead, saves trail behind
-    lookahead = 4
-    with ThreadPoolExecutor(max_workers=2) as loaders, ThreadPoolExecutor(max_workers=4) as writers:
-        loading = {i: loaders.submit(numpy.load, found[i]) for i in range(min(lookahead, len(found)))}
-        saving = []
-        for i, name in enumerate(found):
-            print("File:\t{}".format(name))
-            matrix = loading.pop(i).result()
-            if i + lookahead < len(found):
-                loading[i + lookahead] = loaders.submit(numpy.load, found[i + lookahead])
-            if npy_dtype() is numpy.float64:
-                envelope = ExtractEnvelopeFromMatrix(matrix, LPF, CUTOFF)
-            else:  # opt-in float32 files (F2CNN_B200_NPY_FLOAT32, see GammatoneFiltering)
-                from ... import api
-                envelope = api.extract_envelope_from_matrix(matrix, LPF, CUTOFF, dtype=numpy.float32)
-            saving.append(writers.submit(SaveEnvelope, envelope, name, len(found)))
-            while len(saving) > 8:
-                saving.pop(0).result()
-        for job in saving:
+    # one thread drives the GPU; matrix loads run a few files ahead, the envelopes of a batch land in one of
+    # two pinned host slots and the writer threads save straight from there
+    from ... import api
+    stream = api.MatrixStream(None, "envelope", LPF=LPF, CUTOFF=CUTOFF, dtype=npy_dtype())
+    lookahead = 8
+    with ThreadPoolExecutor(max_workers=4) as loaders, ThreadPoolExecutor(max_workers=8) as writers:
+        loading, submitted = {}, 0
+
+        def matrix_of(i):
+            nonlocal submitted
+            while submitted < min(len(found), i + lookahead):
+                loading[submitted] = loaders.submit(numpy.load, found[submitted])
+                submitted += 1
+            return loading[i].result()
+
+        pending = []
+        i = 0
+        while i < len(found):
+            group, used = [], 0
+            while i < len(found):
+                matrix = matrix_of(i)
+                need = matrix.size * stream.per_value
+                if group and used + need > stream.slot_bytes:
+                    break
+                print("File:\t{}".format(found[i]))
+                group.append((found[i], matrix))
+                used += need
+                del loading[i]
+                i += 1
+            envelopes = stream.process([m for _, m in group])
+            jobs = [writers.submit(SaveEnvelope, e, name, len(found)) for (name, _), e in zip(group, envelopes)]
+            stream.retire(jobs)
+            pending.extend(jobs)
+        for job in pending:
             job.result()
     print("Extracted Envelopes from all files.")
     print('              Total time:', time.time() - started)

@@ -142,19 +142,25 @@ def FilterAllOrganisedFiles():
     print(len(found), "files found")
 
     InitProcesses(_configured_bank(), Value('i', 0))
-    in_flight = []
-    with ThreadPoolExecutor(max_workers=4) as writers:
-        for wav in found:
-            print("Filtering:\t{}".format(wav))
-            if npy_dtype() is numpy.float64:
-                matrix, _ = GetFilteredOutputFromFile(wav, FILTERBANK_COEFFICIENTS)
-            else:
-                from ... import api
-                matrix = api.erb_filterbank(GetArrayFromWAV(wav)[1], FILTERBANK_COEFFICIENTS, dtype=numpy.float32)
-            in_flight.append(writers.submit(_store, wav, matrix, len(found)))
-            while len(in_flight) > 8:  # bound the host memory held by queued 49 MB matrices
-                in_flight.pop(0).result()
-        for job in in_flight:
+    # Many utterances per launch sequence: the matrices of a batch land in one of two pinned host slots and
+    # the writer threads save straight from there while the next batch is read, filtered and downloaded.
+    from ... import api
+    stream = api.MatrixStream(FILTERBANK_COEFFICIENTS, "filterbank", dtype=npy_dtype())
+    channels = FILTERBANK_COEFFICIENTS.shape[0]
+    with ThreadPoolExecutor(max_workers=8) as readers, ThreadPoolExecutor(max_workers=8) as writers:
+        pending = []
+        chunk = 64   # files decoded ahead, regrouped into slot-sized batches below
+        for lo in range(0, len(found), chunk):
+            names = found[lo:lo + chunk]
+            waves = [samples for _, samples in readers.map(GetArrayFromWAV, names)]
+            for group in stream.batches([channels * len(w) for w in waves]):
+                for i in group:
+                    print("Filtering:\t{}".format(names[i]))
+                matrices = stream.process([waves[i] for i in group])
+                jobs = [writers.submit(_store, names[i], m, len(found)) for i, m in zip(group, matrices)]
+                stream.retire(jobs)
+                pending.extend(jobs)
+        for job in pending:
             job.result()
     print("Filtered and Saved all files.")
     print('                Total time:', time.time() - started)
