@@ -337,6 +337,12 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # nvidia-smi samples every 100 ms and a sharded step lasts a few ms: keep the device under the same load
+    # (untimed steps) until the sampler has seen it, then time
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:
+        step()
+        torch.cuda.synchronize()
     ev = [(engine.DeviceEvent(), engine.DeviceEvent()) for _ in range(args.steps)]
     t_start, t_stop = engine.DeviceEvent(), engine.DeviceEvent()
     barrier()
@@ -406,6 +412,10 @@ def main():
                 fresh_ms.append((time.perf_counter() - t0) * 1e3)
                 del tmp
         barrier()
+        pipe_subs = None
+        with api._pipelines_lock:
+            for p_ in api._pipelines.values():
+                pipe_subs = (len(p_.subs), p_.placer.threads)
         verified = None
         if rank == 0:
             # the host path must produce exactly what the resident path produced ...
@@ -419,10 +429,6 @@ def main():
                 assert verified, "sharded result differs from the single-GPU result"
                 del one
         barrier()
-        pipe_subs = None
-        with api._pipelines_lock:
-            for p_ in api._pipelines.values():
-                pipe_subs = (len(p_.subs), p_.placer.threads)
         my_frames = int(np.sum((my_lengths + STEP - 1) // STEP))
         e2e = {"value": cs_per_step / (ms_e2e * 1e-3), "unit": "channel-samples/s",
                "h2d_bytes_per_step": total_samples * 2,

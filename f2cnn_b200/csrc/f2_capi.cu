@@ -617,8 +617,13 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
         if (!a->win_offsets || a->win_dots < 1)
             return fail(F2_ERR_INVALID, "f2_batch_run: `windows` needs win_offsets and win_dots >= 1");
     }
-    const bool want_gfb = a->gfb != nullptr;
-    const bool want_env_scratch = a->env != nullptr && a->env_t == nullptr;
+    // (C, n) outputs: written by the fused kernel itself through a shared-memory transpose, unless the
+    // time-major envelope is wanted as well -- then the envelope is computed once into env_t and transposed
+    // (and the filterbank output takes the same route)
+    const bool direct_cn = (a->gfb != nullptr || a->env != nullptr) && a->env_t == nullptr &&
+                           (a->gfb == nullptr || a->env == nullptr || a->gfb_dtype == a->env_dtype);
+    const bool want_gfb = a->gfb != nullptr && !direct_cn;
+    const bool want_env_scratch = a->env != nullptr && a->env_t == nullptr && !direct_cn;
     const size_t need = f2_batch_workspace_bytes(b, want_gfb, want_env_scratch);
     if (!workspace || workspace_bytes < need)
         return fail(F2_ERR_WORKSPACE, "workspace %zu bytes, need %zu", workspace_bytes, need);
@@ -650,7 +655,7 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
         env_t = (float*)cur;
         cur += ws_full_bytes(b);
     }
-    const bool need_env = env_t != nullptr || a->dec != nullptr || a->windows != nullptr;
+    const bool need_env = env_t != nullptr || a->dec != nullptr || a->windows != nullptr || (direct_cn && a->env != nullptr);
 
     f2::PrepParams pp;
     pp.utts = b->d_utts;
@@ -670,13 +675,16 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     f2::FusedParams fp;
     fp.utts = b->d_utts;
     // the filterbank output is store-bound and uses the direct form for fewer groups: equal-length chunks
-    const bool uniform_chunks = gfb_t != nullptr && b->d_items_uniform != nullptr;
+    const bool uniform_chunks = (gfb_t != nullptr || (direct_cn && a->gfb != nullptr)) && b->d_items_uniform != nullptr;
     fp.items = uniform_chunks ? b->d_items_uniform : b->d_items;
     fp.chan = plan->d_chan;
     fp.xz = xz;
     fp.G = G;
     fp.gfb_t = gfb_t;
     fp.env_t = env_t;
+    fp.gfb_cn = direct_cn ? a->gfb : nullptr;
+    fp.env_cn = direct_cn ? a->env : nullptr;
+    fp.cn_f64 = direct_cn && (a->gfb ? a->gfb_dtype : a->env_dtype) == F2_F64 ? 1 : 0;
     fp.dec = a->dec;
     fp.win = a->windows;
     fp.win_off = reinterpret_cast<const long long*>(a->win_offsets);
@@ -716,10 +724,10 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     F2_CUDA(f2::launch_fused(fp, (int)(uniform_chunks ? b->n_items_uniform : b->n_items), stream));
     if (a->ev_fused_stop) F2_CUDA(cudaEventRecord((cudaEvent_t)a->ev_fused_stop, stream));
 
-    if (a->gfb)
+    if (a->gfb && !direct_cn)
         F2_CUDA(f2::launch_transpose_convert(b->d_utts, b->n_utts, b->max_n, gfb_t, a->gfb, a->gfb_dtype, plan->C,
                                              stream));
-    if (a->env)
+    if (a->env && !direct_cn)
         F2_CUDA(f2::launch_transpose_convert(b->d_utts, b->n_utts, b->max_n, env_t, a->env, a->env_dtype, plan->C,
                                              stream));
     return F2_OK;
@@ -1049,11 +1057,14 @@ int f2_gather_windows_cn(const void* env, int dtype, int n_channels, int64_t n, 
     return F2_OK;
 }
 
-int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int64_t i0, int64_t i1, int normalize,
-                    void* out, int out_dtype, int* bad_flag, void* stream) {
+int f2_dense_frames(const float* env_t, int64_t n_rows, int n_channels, int dots, int step, int64_t i0, int64_t i1,
+                    int normalize, void* out, int out_dtype, int* bad_flag, void* stream) {
     if (i1 <= i0) return F2_OK;
     if (!env_t || !out || n_channels <= 0 || dots <= 0 || step <= 0 || i0 < 0 || (normalize && !bad_flag))
         return fail(F2_ERR_INVALID, "f2_dense_frames: bad arguments");
+    if (i1 + (int64_t)(dots - 1) * step > n_rows)
+        return fail(F2_ERR_INVALID, "f2_dense_frames: frames up to %lld x %d dots of step %d leave the %lld rows of env_t",
+                    (long long)i1, dots, step, (long long)n_rows);
     F2_CUDA(f2::launch_dense_frames(env_t, n_channels, dots, step, i0, i1, normalize, out, out_dtype, bad_flag,
                                     (cudaStream_t)stream));
     return F2_OK;

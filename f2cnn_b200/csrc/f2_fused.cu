@@ -212,7 +212,34 @@ struct OutCtx {
     float env_scale;  // g4 (no low-pass) or g4*b0 (low-pass): applied when a value is stored
     int wk;         // OUT 3: index (within the utterance) of the next decimated frame
     int nwin;       // OUT 3: windows of this utterance
+    // CN: (C, n) outputs in the reference's layout.  Each lane stages its channel's samples in a 32 x 33
+    // shared-memory tile; every 32 samples the warp writes the tile out row by row -- 32 consecutive samples
+    // of one channel per store instruction (128 / 256 contiguous bytes) instead of a time-major scratch
+    // matrix and a transposing second kernel.
+    float* tr_g;    // shared-memory tiles (or null)
+    float* tr_e;
+    char* cn_g;     // element (first channel of this CTA, sample 0) of the utterance's (C, n) block (or null)
+    char* cn_e;
+    int cn_n;       // samples per row
+    int cn_rows;    // channels of this CTA that exist (<= 32)
+    int cn_f64;
 };
+
+// rows of the staged tile -> global: samples [tb, tb + cnt) of every channel of this CTA
+__device__ __forceinline__ void flush_cn(const float* tr, char* base, const OutCtx& o, int tb, int cnt) {
+    __syncwarp();
+    const int lane = threadIdx.x;
+    if (o.cn_f64) {
+        double* row = reinterpret_cast<double*>(base) + tb + lane;
+        for (int r = 0; r < o.cn_rows; ++r, row += o.cn_n)
+            if (lane < cnt) __stcs(row, (double)tr[r * 33 + lane]);
+    } else {
+        float* row = reinterpret_cast<float*>(base) + tb + lane;
+        for (int r = 0; r < o.cn_rows; ++r, row += o.cn_n)
+            if (lane < cnt) __stcs(row, tr[r * 33 + lane]);
+    }
+    __syncwarp();
+}
 
 // OUT 3: decimated frame j = o.wk with value v goes to slot s of window j-s, s < dots, where that
 // window exists: ((row0 + j - s)*dots + s)*C = (row0 + j)*dots*C - s*(dots-1)*C.  dots and C are
@@ -248,7 +275,7 @@ __device__ __forceinline__ float envelope(const FusedParams& p, State& s, float2
     return e;
 }
 
-template <int FORM, int ENV, int OUT, bool ZEROX, int U>
+template <int FORM, int ENV, int OUT, bool ZEROX, int U, bool CN = false>
 __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, State& s, const float (&ee)[4],
                                          const float (&eo)[4], const float2* __restrict__ sxz,
                                          const float* __restrict__ sg, int t, int cnt, bool active, OutCtx& o) {
@@ -279,18 +306,30 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             const float2 u = make_float2(ZEROX ? 0.f : xv[2 * j], xv[2 * j + 1]);
             const float2 y = (j & 1) ? cascade<FORM>(k, s, u, gv[j], eo) : cascade<FORM>(k, s, u, gv[j], ee);
             if (ENV > 0) ev[j] = envelope<ENV>(p, s, y);
-            if (OUT == 2) {
+            if (OUT == 2 && !CN) {
                 if (o.gfb && active) __stcs(o.gfb + (size_t)j * o.C, k.g4 * y.x);
                 if (ENV > 0 && o.env && active) {
                     const float v = ENV == 2 ? ev[j] + (j > 0 ? ev[j > 0 ? j - 1 : 0] : wprev) : ev[j];
                     __stcs(o.env + (size_t)j * o.C, o.env_scale * v);
                 }
             }
+            if (OUT == 2 && CN) {
+                const int col = (t + i + j) & 31;
+                if (o.cn_g) o.tr_g[threadIdx.x * 33 + col] = k.g4 * y.x;
+                if (ENV > 0 && o.cn_e) {
+                    const float v = ENV == 2 ? ev[j] + (j > 0 ? ev[j > 0 ? j - 1 : 0] : wprev) : ev[j];
+                    o.tr_e[threadIdx.x * 33 + col] = o.env_scale * v;
+                }
+            }
         }
         if (ENV == 2) s.wprev = ev[U - 1];
-        if (OUT == 2) {
+        if (OUT == 2 && !CN) {
             if (o.gfb) o.gfb += U * o.C;
             if (o.env) o.env += U * o.C;
+        }
+        if (OUT == 2 && CN && ((t + i + U) & 31) == 0) {
+            if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + i + U - 32, 32);
+            if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + i + U - 32, 32);
         }
         if (OUT > 0 && ENV > 0 && o.dec) {
             while (o.next_dec < t + i + U) {
@@ -321,7 +360,7 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
         if (ENV > 0) e = envelope<ENV>(p, s, y);
         const float out = ENV == 2 ? e + s.wprev : e;
         if (ENV == 2) s.wprev = e;
-        if (OUT == 2) {
+        if (OUT == 2 && !CN) {
             if (o.gfb) {
                 if (active) __stcs(o.gfb, k.g4 * y.x);
                 o.gfb += o.C;
@@ -329,6 +368,15 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             if (ENV > 0 && o.env) {
                 if (active) __stcs(o.env, o.env_scale * out);
                 o.env += o.C;
+            }
+        }
+        if (OUT == 2 && CN) {
+            const int col = (t + i) & 31;
+            if (o.cn_g) o.tr_g[threadIdx.x * 33 + col] = k.g4 * y.x;
+            if (ENV > 0 && o.cn_e) o.tr_e[threadIdx.x * 33 + col] = o.env_scale * out;
+            if (col == 31) {
+                if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + i - 31, 32);
+                if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + i - 31, 32);
             }
         }
         if (OUT > 0 && ENV > 0 && o.dec && o.next_dec == t + i) {
@@ -341,18 +389,24 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             o.next_dec += o.step;
         }
     }
+    if (OUT == 2 && CN && ((t + cnt) & 31) != 0) {   // the utterance ends inside a block of 32
+        const int rest = (t + cnt) & 31;
+        if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + cnt - rest, rest);
+        if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + cnt - rest, rest);
+    }
 }
 
 struct Smem {
     float2 (*xz)[kTile];
     float (*g)[kTile];
     uint64_t* full;
+    float* tr;   // CN: two 32 x 33 transposition tiles
 };
 
 // The whole CTA (= one warp = 32 adjacent channels) for one section form.
 // EDGE: the edge residuals come from the per-utterance table (time-chunked batches) instead of
 // the in-kernel pass.
-template <int FORM, int U, bool EDGE, bool WIN>
+template <int FORM, int U, bool EDGE, bool WIN, bool CN>
 __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& item, const Smem& sm, const int c) {
     const UttDesc ut = p.utts[item.utt];
     const int tid = threadIdx.x;
@@ -387,10 +441,10 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
     const int t0 = item.t0, t1 = item.t1;
     int tE0 = n - p.w_edge;
     tE0 = tE0 > 0 ? (tE0 / kTile) * kTile : 0;
-    const bool need_env = WIN || p.env_t != nullptr || p.dec != nullptr;
+    const bool need_env = WIN || p.env_t != nullptr || p.dec != nullptr || (CN && p.env_cn != nullptr);
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
     // WIN: the window-store instantiation (f2_run_args.windows; no full-rate outputs by contract)
-    const bool full_out = !WIN && (p.gfb_t != nullptr || p.env_t != nullptr);
+    const bool full_out = !WIN && (CN || p.gfb_t != nullptr || p.env_t != nullptr);
     const int nE = (need_imag && !EDGE) ? (n - tE0 + kTile - 1) / kTile : 0;
     const int w_lpf = (p.lpf && need_env) ? p.w_lpf : 0;
     int ts, tenv;
@@ -436,6 +490,21 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
     o.env_scale = p.lpf ? k.g4 * p.lp_b0 : k.g4;
     o.gfb = p.gfb_t ? p.gfb_t + (size_t)(ut.full_off + t0) * o.C + (active ? c : 0) : nullptr;
     o.env = p.env_t ? p.env_t + (size_t)(ut.full_off + t0) * o.C + (active ? c : 0) : nullptr;
+    o.tr_g = o.tr_e = nullptr;
+    o.cn_g = o.cn_e = nullptr;
+    o.cn_n = n;
+    o.cn_f64 = p.cn_f64;
+    o.cn_rows = 0;
+    if (CN) {
+        const int c0 = item.cblock * kChanPerBlock;
+        o.cn_rows = min(kChanPerBlock, p.C - c0);
+        const size_t esize = p.cn_f64 ? 8 : 4;
+        const size_t block = ((size_t)ut.full_off * o.C + (size_t)c0 * (size_t)n) * esize;   // (C, n_u) blocks back to back
+        o.tr_g = sm.tr;
+        o.tr_e = sm.tr + 32 * 33;
+        o.cn_g = p.gfb_cn ? reinterpret_cast<char*>(p.gfb_cn) + block : nullptr;
+        o.cn_e = p.env_cn ? reinterpret_cast<char*>(p.env_cn) + block : nullptr;
+    }
     {
         // first decimated frame at or after t0: t = phase + j*step
         int j0 = 0;
@@ -501,9 +570,9 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
             } else if (full_out) {
                 // full-rate stores: the 8-sample unroll is the faster one (3.9 vs 4.9 ms on 256 utterances)
                 constexpr int UF = U < 8 ? U : 8;
-                if (p.lpf) run_tile<FORM, 2, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else if (need_env) run_tile<FORM, 1, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
-                else run_tile<FORM, 0, 2, false, UF>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                if (p.lpf && need_env) run_tile<FORM, 2, 2, false, UF, CN>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else if (need_env) run_tile<FORM, 1, 2, false, UF, CN>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
+                else run_tile<FORM, 0, 2, false, UF, CN>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
             } else if (WIN) {
                 if (p.lpf) run_tile<FORM, 2, 3, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
                 else run_tile<FORM, 1, 3, false, U>(p, k, s, ee, eo, sxz, sg, t, cnt, active, o);
@@ -521,12 +590,13 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
 // separate straight-line programs behind one branch, and a warp that finishes early (direct
 // form: 3 FMAs per section instead of 4) frees its slot for the next work item instead of
 // waiting at a CTA barrier for slower warps (measured: DESIGN.md section 6).
-template <int MINB, int U, bool EDGE, bool WIN>
+template <int MINB, int U, bool EDGE, bool WIN, bool CN>
 __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedParams p) {
     static_assert(kChanPerBlock == 32, "one warp per CTA: __syncwarp is the only barrier used");
     __shared__ __align__(128) float2 s_xz[kStages][kTile];
     __shared__ __align__(128) float s_g[kStages][kTile];
     __shared__ __align__(8) uint64_t s_full[kStages];
+    __shared__ float s_tr[CN ? 2 * 32 * 33 : 1];
     if (threadIdx.x == 0) {
         for (int b = 0; b < kStages; ++b) mbar_init(&s_full[b], 1);
         mbar_fence_init();
@@ -534,26 +604,30 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     __syncwarp();
     const Item item = p.items[blockIdx.x];
     const int c = item.cblock * kChanPerBlock + threadIdx.x;
-    const Smem sm{s_xz, s_g, s_full};
+    const Smem sm{s_xz, s_g, s_full, s_tr};
     // per group of 32 channels (c_pad = C rounded up to 32): min over the group of 1 + B1 + B2
     const float group_cy = p.chan[P_FORM * p.c_pad + c];
 #ifdef F2_SINGLE_FORM
     (void)group_cy;
-    fused_body<F2_SINGLE_FORM, U, EDGE, WIN>(p, item, sm, c);
+    fused_body<F2_SINGLE_FORM, U, EDGE, WIN, CN>(p, item, sm, c);
 #else
-    if (group_cy >= p.direct_min_cy) fused_body<1, U, EDGE, WIN>(p, item, sm, c);
-    else fused_body<0, U, EDGE, WIN>(p, item, sm, c);
+    if (group_cy >= p.direct_min_cy) fused_body<1, U, EDGE, WIN, CN>(p, item, sm, c);
+    else fused_body<0, U, EDGE, WIN, CN>(p, item, sm, c);
 #endif
 }
 
 template <int MINB, int U>
 static void launch_variant(const FusedParams& p, int n_items, cudaStream_t stream) {
     if (p.win) {
-        if (p.edge) fused_kernel<MINB, U, true, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
-        else fused_kernel<MINB, U, false, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        if (p.edge) fused_kernel<MINB, U, true, true, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        else fused_kernel<MINB, U, false, true, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+    } else if (p.gfb_cn || p.env_cn) {
+        // (C, n) outputs written by the kernel itself (own instantiation: two transposition tiles per CTA)
+        if (p.edge) fused_kernel<MINB, U, true, false, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        else fused_kernel<MINB, U, false, false, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
     } else {
-        if (p.edge) fused_kernel<MINB, U, true, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
-        else fused_kernel<MINB, U, false, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        if (p.edge) fused_kernel<MINB, U, true, false, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        else fused_kernel<MINB, U, false, false, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
     }
 }
 

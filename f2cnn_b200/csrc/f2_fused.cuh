@@ -12,6 +12,9 @@ struct FusedParams {
     const float* G;      // rings: circular Hilbert kernel aligned to each utterance's edge
     float* gfb_t;        // full-rate filterbank output, time-major [t][C]   (nullable)
     float* env_t;        // full-rate envelope, time-major [t][C]            (nullable)
+    void* gfb_cn;        // full-rate filterbank output in the REFERENCE layout: (C, n_u) blocks back to back,
+    void* env_cn;        //   float64 or float32 -- stored by the kernel through a shared-memory transpose (nullable)
+    int cn_f64;          // element type of gfb_cn / env_cn: 1 = float64, 0 = float32
     float* dec;          // decimated envelope frames [frame][C]             (nullable)
     float* win;          // windows of win_dots consecutive frames [row][win_dots][C]   (nullable)
     const long long* win_off;  // [n_utts+1] first window row of each utterance

@@ -310,7 +310,9 @@ def dense_frames(env_t_dev, dots, step, i0, i1, normalize=False, out_dtype=torch
     C = int(env_t_dev.shape[1])
     out = torch.empty((max(i1 - i0, 0), dots, C), dtype=out_dtype, device=env_t_dev.device)
     flag = torch.zeros(1, dtype=torch.int32, device=env_t_dev.device)
-    check(_native.lib().f2_dense_frames(_ptr(env_t_dev), C, int(dots), int(step), int(i0), int(i1),
+    if not env_t_dev.is_contiguous() or env_t_dev.dtype != torch.float32:
+        raise ValueError("dense_frames wants a contiguous float32 [rows, C] envelope")
+    check(_native.lib().f2_dense_frames(_ptr(env_t_dev), int(env_t_dev.shape[0]), C, int(dots), int(step), int(i0), int(i1),
                                         int(bool(normalize)), _ptr(out), _T2F2[out_dtype], _ptr(flag),
                                         _stream_ptr(stream)))
     return out, flag

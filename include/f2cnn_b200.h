@@ -157,9 +157,10 @@ F2_API int f2_gather_windows_cn(const void* env, int dtype, int n_channels, int6
                                 int64_t n_idx, float* out, void* stream);
 /* Dense framing of Evaluating.py:70-78: frame i = env_t rows i + k*step, k < dots, for
  * i0 <= i < i1; normalize != 0 applies Training.normalizeInput (Training.py:13-28) per frame
- * and sets *bad_flag (device int) when a frame has a value <= 0 (the reference raises). */
-F2_API int f2_dense_frames(const float* env_t, int n_channels, int dots, int step, int64_t i0, int64_t i1, int normalize,
-                    void* out, int out_dtype, int* bad_flag, void* stream);
+ * and sets *bad_flag (device int) when a frame has a value <= 0 (the reference raises).
+ * n_rows: rows of env_t; frames that would read past it are rejected (F2_ERR_INVALID). */
+F2_API int f2_dense_frames(const float* env_t, int64_t n_rows, int n_channels, int dots, int step, int64_t i0, int64_t i1,
+                    int normalize, void* out, int out_dtype, int* bad_flag, void* stream);
 
 /* ---- host side of the window stage ---------------------------------------------------------
  * All pointers in this section are HOST pointers and none of these functions needs a device.

@@ -531,3 +531,24 @@ def test_banks_outside_the_float32_tolerance_raise_instead_of_answering(gpu, ora
     # the configured bank and its neighbours stay far inside
     for low, width in ((100, 1.0), (100, 2.0), (50, 1.0)):
         assert engine.bank_check(filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, low), width))[0] < 0.5
+
+
+def test_degenerate_requests_of_the_pipeline_and_the_framing(gpu):
+    """No utterances / no windows through the corpus pipeline, and dense frames that would read past the
+    envelope (the C ABI takes bare pointers: the bound travels with the call)."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import _native
+    plan = engine.plan_for(coefs128())
+    pipe = engine.WindowPipeline(plan, np.zeros(0, dtype=np.int64))
+    assert pipe.subs == [] and pipe.total_frames == 0
+    out = np.zeros((0, 11, 128), np.float32)
+    pipe.run(torch.zeros(0, dtype=torch.int16), np.zeros((0, 3), np.int64), out)
+    pipe = engine.WindowPipeline(plan, [3000, 1200])            # too short for any window
+    runs, _, n_rows = engine.window_runs(np.zeros(0, np.int64), [0, 0], [3000, 1200], pipe.frame_offsets)
+    assert n_rows == 0 and runs.shape == (0, 3)
+    pipe.run(torch.zeros(4200, dtype=torch.int16).pin_memory(), runs, out)
+    env_t = torch.rand((2000, 128), device="cuda") + 0.1
+    frames, flag = engine.dense_frames(env_t, 11, 160, 0, 2000 - 1760 + 160)
+    assert frames.shape[0] == 400 and int(flag.item()) == 0
+    with pytest.raises(_native.F2Error):
+        engine.dense_frames(env_t, 11, 160, 0, 401)
