@@ -8,7 +8,7 @@ import sys
 
 tag = sys.argv[1]
 launches = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/launches.csv"
-rep = sys.argv[3] if len(sys.argv) > 3 else None
+reps = sys.argv[3:]
 out = ["# ncu summary %s" % tag, ""]
 rows = list(csv.reader(open(launches)))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -26,7 +26,7 @@ out += ["## launch list (`ncu --metrics gpu__time_duration.sum --clock-control n
         "compare shares)", "", "| kernel | launches | mean ms | share |", "|---|---:|---:|---:|"]
 for k, v in agg.items():
     out.append("| `%s` | %d | %.3f | %.1f%% |" % (k, len(v), sum(v) / len(v), 100 * sum(v) / tot))
-if rep:
+for rep in reps:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     Hh, Uu = rr[0], rr[1]
@@ -47,8 +47,11 @@ if rep:
             "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
-    for row in rr[2:]:
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
+    for row in rr[2:3]:
         name = row[Hh.index("Kernel Name")] if "Kernel Name" in Hh else "?"
         out += ["", "## `ncu --set full` of `%s`" % name.split("(")[0], "", "| metric | unit | value |", "|---|---|---:|"]
         for h, u, v in zip(Hh, Uu, row):
