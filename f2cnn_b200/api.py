@@ -280,7 +280,8 @@ def _pipeline_for(plan, lengths, dots, step, phase, LPF, CUTOFF, src_offsets=Non
         pipe = _pipelines.get(key)
         if pipe is None:
             # `share` processes of this box run a pipeline each: split the host cores between their pools
-            threads = max(1, engine.host_cores() // max(int(share), 1))
+            # (one core stays free for the CUDA host-callback thread that hands frames to the pool)
+            threads = max(1, engine.host_cores() // max(int(share), 1) - (1 if int(share) == 1 else 0))
             pipe = engine.WindowPipeline(plan, lengths, dots=dots, step=step, phase=phase, lpf=LPF, cutoff=CUTOFF,
                                          src_offsets=src_offsets, placer=engine.Placer(threads))
             _pipelines[key] = pipe
@@ -375,19 +376,38 @@ def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=
             src_offsets = (np.cumsum(lengths) - lengths)[sel]
             row_offsets = (np.cumsum(counts) - counts)[sel]
             share = world
-        n_dec = np.where(lens > phase, (lens - phase + step - 1) // step, 0)
-        frame_offsets = np.concatenate([[0], np.cumsum(n_dec)]).astype(np.int64)
-        runs, phase2, _ = engine.window_runs(cen, cnts, lens, frame_offsets, radius, step, phase, row_offsets=row_offsets)
-        if runs is not None and phase2 == phase:
-            pipe = _pipeline_for(plan, lens, dots, step, phase, LPF, CUTOFF, src_offsets, share)
-            result = engine.host_empty((total, dots, C), np.float32) if out is None else out
-            if flat_in is not None:
-                pipe.run(flat_in, runs, result)
-            else:
-                pipe.run(waves if shard is None else [waves[u] for u in sel], runs, result)
+        # cheap look at the first utterances before anything is built: a request that is not on one grid
+        # goes straight to the general path
+        head = int(min(8, cnts.shape[0]))
+        n_dec_h = np.where(lens[:head] > phase, (lens[:head] - phase + step - 1) // step, 0)
+        probe, phase_h, _ = engine.window_runs(cen[:int(cnts[:head].sum())], cnts[:head], lens[:head],
+                                               np.concatenate([[0], np.cumsum(n_dec_h)]), radius, step, phase)
+        on_one_grid = probe is not None and phase_h == phase
+    else:
+        on_one_grid = False
+    if on_one_grid:
+        pipe = _pipeline_for(plan, lens, dots, step, phase, LPF, CUTOFF, src_offsets, share)
+        result = engine.host_empty((total, dots, C), np.float32) if out is None else out
+        state = {}
+
+        def detect():
+            # runs on the host while the first sub-batch is already on the device
+            runs, phase2, _ = engine.window_runs(cen, cnts, lens, pipe.frame_offsets, radius, step, phase,
+                                                 row_offsets=row_offsets)
+            state["ok"] = runs is not None and phase2 == phase
+            return runs if state["ok"] else np.zeros((0, 3), dtype=np.int64)
+
+        if flat_in is not None:
+            pipe.run(flat_in, detect, result)
+        else:
+            pipe.run(waves if shard is None else [waves[u] for u in sel], detect, result)
+        if state["ok"]:
             return result
-        if shard is not None:
-            raise ValueError("shard= needs timepoints that are windows of consecutive frames of one decimated grid")
+        # legal timepoints that are not windows of consecutive frames of one grid (a wrapping index, mixed
+        # phases) further down the corpus: nothing was placed; the general path below answers
+        del result
+    if shard is not None:
+        raise ValueError("shard= needs timepoints that are windows of consecutive frames of one decimated grid")
 
     # general path: one batch, windows gathered on the device
     cpos = np.concatenate([[0], np.cumsum(counts)])

@@ -445,6 +445,7 @@ class WindowPipeline:
             self._ev_done = [torch.cuda.Event(enable_timing=True) for _ in self.subs]
             self._ev_out = [torch.cuda.Event(enable_timing=True) for _ in self.subs]
             self._ev_start = torch.cuda.Event(enable_timing=True)
+            self._ev_end = torch.cuda.Event(blocking=True)
         self.timing = False     # True: run() synchronises first and keeps a timeline (see timeline())
         self._t0 = None
         self.placer = placer if placer is not None else Placer()
@@ -497,7 +498,6 @@ class WindowPipeline:
             self._wave_dev = torch.empty(max(self.total_samples, 1), dtype=dt, device=dev)
         if not pinned and (self._stage is None or self._stage.dtype != dt):
             self._stage = _pinned_empty(self.total_samples, dt)
-        per_sub = self._split_runs(runs)
         out_flat = out_host
         esize = self._wave_dev.element_size()
         if self.timing:
@@ -534,15 +534,24 @@ class WindowPipeline:
             sub["batch"].run(self._wave_dev[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff, out={"dec": dec},
                              stream=comp)
             self._ev_done[i].record(comp)
-            with torch.cuda.stream(self._s_out):
+        # Uploads and kernels of every sub-batch are queued; only now is the placement plan needed.  `runs`
+        # may be a callable: the run detection of a corpus (a few ms on the host) then happens while the
+        # first sub-batch is already being filtered.
+        if callable(runs):
+            runs = runs()
+        per_sub = self._split_runs(runs)
+        with torch.cuda.stream(self._s_out):
+            for i, sub in enumerate(self.subs):
                 self._s_out.wait_event(self._ev_done[i])
                 if sub["f1"] > sub["f0"]:
-                    self._dec_host[sub["f0"]:sub["f1"]].copy_(dec, non_blocking=True)
+                    self._dec_host[sub["f0"]:sub["f1"]].copy_(self._dec_dev[sub["f0"]:sub["f1"]], non_blocking=True)
                 self._ev_out[i].record(self._s_out)
                 if per_sub[i].shape[0]:
                     self.placer.submit(self._dec_host, per_sub[i], out_flat, dots=self.dots, stream=self._s_out)
+            self._ev_end.record(self._s_out)
         for s_ in (self._s_out, self._s_comp[0], self._s_comp[1]):
             caller.wait_stream(s_)
+        self._ev_end.synchronize()      # blocking event: the waiting thread sleeps, its core places rows
         self._s_out.synchronize()
         self.placer.wait()
         return out_host

@@ -552,3 +552,46 @@ def test_degenerate_requests_of_the_pipeline_and_the_framing(gpu):
     assert frames.shape[0] == 400 and int(flag.item()) == 0
     with pytest.raises(_native.F2Error):
         engine.dense_frames(env_t, 11, 160, 0, 401)
+
+
+def test_corpus_pipeline_input_forms_out_argument_and_fallthrough(gpu, monkeypatch):
+    """The pipelined path of features_to_windows: pinned flat buffer, pageable flat buffer and list of arrays
+    give the same bits; out= is filled in place and validated; timepoints in flat (centres, counts) form;
+    a request whose LATER utterances leave the grid (a wrapping window) falls through to the general path."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = coefs128()
+    lengths = synth.corpus_lengths(40, lo=6000, hi=15000, seed=6)
+    waves = [synth.white_noise_i16(int(n), seed=300 + i) for i, n in enumerate(lengths)]
+    tps = [synth.label_grid(int(n)) for n in lengths]
+    flat = np.concatenate(waves)
+    counts = np.asarray([len(t) for t in tps])
+    monkeypatch.setattr(api, "_PIPELINE_BYTES", 1)
+    a = api.features_to_windows((torch.from_numpy(flat).pin_memory(), lengths), co, tps, True, 50)
+    b = api.features_to_windows((flat, lengths), co, np.concatenate(tps), True, 50, counts=counts)
+    c = api.features_to_windows(waves, co, tps, True, 50)
+    assert a.shape == (counts.sum(), 11, 128) and np.array_equal(a, b) and np.array_equal(a, c)
+    out = np.full_like(a, np.nan)
+    assert api.features_to_windows((flat, lengths), co, tps, True, 50, out=out) is out and np.array_equal(out, a)
+    with pytest.raises(ValueError):
+        api.features_to_windows((flat, lengths), co, tps, True, 50, out=np.zeros((3, 11, 128), np.float32))
+    with pytest.raises(ValueError):
+        api.features_to_windows((flat, lengths), co, tps, True, 50, shard=(0, 2))      # shard needs the shared out
+    # shards of a 3-way split into one array == the whole
+    parts = np.zeros_like(a)
+    for r in range(3):
+        api.features_to_windows((flat, lengths), co, tps, True, 50, out=parts, shard=(r, 3))
+    assert np.array_equal(parts, a)
+    # utterance 20 gets a window that wraps like a negative Python index: legal, but not a run of frames
+    tps2 = [t.copy() for t in tps]
+    tps2[20] = np.concatenate([[160], tps2[20]])
+    d = api.features_to_windows(waves, co, tps2, True, 50)
+    row20 = int(counts[:20].sum())
+    scale = np.sqrt(np.mean(a.astype(np.float64) ** 2, axis=(0, 1)))[None, None, :]
+    assert d.shape[0] == a.shape[0] + 1
+    # same values as the pipelined result up to float32 noise (the single batch splits utterances in time)
+    assert np.max(np.abs(np.delete(d, row20, axis=0) - a) / scale) <= 5e-5
+    with pytest.raises(IndexError):
+        bad = [t.copy() for t in tps]
+        bad[30] = np.concatenate([bad[30], [int(lengths[30]) - 100]])
+        api.features_to_windows(waves, co, bad, True, 50)
