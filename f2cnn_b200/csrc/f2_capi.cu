@@ -316,6 +316,17 @@ int f2_plan_create(const double* coefs, int n_channels, int device, f2_plan** ou
         }
         for (int c = g0; c < g0 + 32; ++c) par[(size_t)f2::P_FORM * c_pad + c] = (float)cy;
     }
+    // Per group: how much sooner than the bank's slowest channel the group's slowest channel forgets
+    // (ratio of -ln|pole|, rounded up a little so that float32 never shortens a length).
+    for (int g0 = 0; g0 < c_pad; g0 += 32) {
+        double nlr = 1e300;
+        for (int c = g0; c < std::min(C, g0 + 32); ++c) {
+            const double* k = coefs + (size_t)c * 10;
+            nlr = std::min(nlr, -0.5 * log(k[8] / k[6]));
+        }
+        const float scale = (float)std::min(1.0, min_nlr / nlr * (1.0 + 1e-6));
+        for (int c = g0; c < g0 + 32; ++c) par[(size_t)f2::P_WSCALE * c_pad + c] = scale;
+    }
     {
         // a bank whose float32 result would leave the stated tolerance is refused, not answered quietly
         int bad = 0;
@@ -462,29 +473,29 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         seg = (long long)align_up((size_t)best, f2::kTile);
     }
     // Chunks of equal COST, not equal length (automatic policy only): a direct-form group runs a
-    // sample in kDirectCost of a delta-form group's time, so its chunks are longer --
-    // (seg_direct + W) * kDirectCost = seg_delta + W, W = the warm-up every chunk pays -- with the
-    // total number of chunks unchanged.  With about one wave of CTAs (a single long stream) all CTAs
-    // then finish together instead of the delta-form ones finishing last.
+    // sample in kDirectCost of a delta-form group's time and every group pays its own warm-up W_g per
+    // chunk (group_warmup), so  (seg_g + W_g) * cost_g = T  for all groups, with T such that the total
+    // number of chunks stays what equal chunks of `seg` samples would give.  With about one wave of
+    // CTAs (a single long stream) all CTAs then finish together instead of the slow groups finishing last.
     std::vector<long long> seg_of((size_t)cblocks, seg);
-    if (target_items <= 0 && seg < ((long long)1 << 40)) {
-        int n_direct = 0;
-        std::vector<char> direct((size_t)cblocks, 0);
+    if (target_items <= 0 && seg < ((long long)1 << 40) && cblocks > 1) {
+        std::vector<double> cost((size_t)cblocks), W((size_t)cblocks);
         for (int cb = 0; cb < cblocks; ++cb) {
-            direct[(size_t)cb] = plan->h_chan[(size_t)f2::P_FORM * plan->c_pad + (size_t)cb * 32] >= kDirectMinCyEnv;
-            n_direct += direct[(size_t)cb];
+            const size_t c0 = (size_t)cb * 32;
+            const bool direct = plan->h_chan[(size_t)f2::P_FORM * plan->c_pad + c0] >= kDirectMinCyEnv;
+            cost[(size_t)cb] = direct ? kDirectCost : 1.0;
+            W[(size_t)cb] = (double)f2::group_warmup(plan->w_casc, plan->h_chan[(size_t)f2::P_WSCALE * plan->c_pad + c0]) + 2048.0;
         }
-        if (n_direct > 0 && n_direct < cblocks) {
-            const double fd = (double)n_direct / cblocks, W = (double)plan->w_casc + 2048.0, s0 = (double)seg;
-            double lo = 2048.0, hi = s0;  // seg_delta
-            for (int it = 0; it < 60; ++it) {
-                const double sD = 0.5 * (lo + hi), sd = (sD + W) / kDirectCost - W;
-                if (fd / sd + (1.0 - fd) / sD > 1.0 / s0) lo = sD; else hi = sD;
-            }
-            const long long sD = (long long)align_up((size_t)std::max(2048.0, 0.5 * (lo + hi)), f2::kTile);
-            const long long sd = (long long)align_up((size_t)std::max(2048.0, ((double)sD + W) / kDirectCost - W), f2::kTile);
-            for (int cb = 0; cb < cblocks; ++cb) seg_of[(size_t)cb] = direct[(size_t)cb] ? sd : sD;
+        auto seg_at = [&](double T, int cb) { return std::max(2048.0, T / cost[(size_t)cb] - W[(size_t)cb]); };
+        double lo = 0.0, hi = 4.0 * ((double)seg + (double)plan->w_casc + 2048.0);
+        for (int it = 0; it < 80; ++it) {
+            const double T = 0.5 * (lo + hi);
+            double chunks = 0.0;  // chunks per sample, summed over the groups
+            for (int cb = 0; cb < cblocks; ++cb) chunks += 1.0 / seg_at(T, cb);
+            if (chunks > (double)cblocks / (double)seg) lo = T; else hi = T;
         }
+        for (int cb = 0; cb < cblocks; ++cb)
+            seg_of[(size_t)cb] = (long long)align_up((size_t)seg_at(0.5 * (lo + hi), cb), f2::kTile);
     }
     auto build_items = [&](const std::vector<long long>& segs, bool same_for_all) {
         std::vector<f2::Item> out;

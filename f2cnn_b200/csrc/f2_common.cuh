@@ -10,6 +10,7 @@
 // the path in this package.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace f2 {
@@ -19,7 +20,7 @@ constexpr int kStages = 4;        // TMA pipeline depth
 constexpr int kChanPerBlock = 32;  // channels (threads) per CTA of the fused kernel: one warp
 constexpr int kEdgeChanPerBlock = 128;           // channels (threads) per CTA of the sequential edge kernel
 constexpr int kRingAlign = 256;   // ring allocations are multiples of this many samples
-constexpr int kNumChanPar = 18;   // floats per channel in the parameter block
+constexpr int kNumChanPar = 19;   // floats per channel in the parameter block
 
 // Per-channel parameter block, parameter-major: par[i * c_pad + c].
 //   0      g4      = A0^4 / gain: output scale of the cascade (filters.py:148,174-182,237)
@@ -30,7 +31,20 @@ constexpr int kNumChanPar = 18;   // floats per channel in the parameter block
 //                    channel groups whose poles are far enough from z = 1
 //   17     group_cy = min over the channel's group of 32 of 1 + B1 + B2 (the fused kernel picks
 //                    the section form per group from it)
-enum ChanPar { P_G4 = 0, P_Z = 1, P_CQ = 5, P_NCY = 9, P_NB1 = 13, P_FORM = 17 };
+//   18     group_wscale = (smallest -ln|pole| of the bank) / (smallest -ln|pole| of the channel's group of
+//                    32), in (0, 1]: the group's truncated-history lengths are the plan's times this --
+//                    a group of wide high-frequency channels forgets its past ten times sooner than
+//                    the 100 Hz channels the plan's lengths are derived from
+enum ChanPar { P_G4 = 0, P_Z = 1, P_CQ = 5, P_NCY = 9, P_NB1 = 13, P_FORM = 17, P_WSCALE = 18 };
+
+// A plan-wide truncated-history length scaled to one channel group, in whole tiles (never longer than
+// the plan's, never shorter than one tile).  Host and device use the same expression.
+__host__ __device__ __forceinline__ int group_warmup(int w_plan, float wscale) {
+    const int v = (int)ceilf((float)w_plan * wscale);
+    const int tiles = (v + kTile - 1) / kTile;
+    const int w = (tiles < 1 ? 1 : tiles) * kTile;
+    return w < w_plan ? w : w_plan;
+}
 
 // One utterance (or one matrix row for the stand-alone envelope path).
 struct UttDesc {

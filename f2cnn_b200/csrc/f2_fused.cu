@@ -40,7 +40,10 @@
 // warm-started from zero state w_casc (+ w_lpf) samples earlier; the truncated history is
 // below float32 resolution (pole radius^W).  The same truncation gives the edge residuals
 // (real cascade over the last w_edge samples) and the periodic steady state of the
-// imaginary path (w_imag samples before t=0 on the ring).
+// imaginary path (w_imag samples before t=0 on the ring).  The plan's lengths are those of the
+// bank's slowest channel; every group of 32 channels scales them to its own slowest pole
+// (group_warmup, f2_common.cuh): 256 / 512 / 1024 / 1536 samples for the four groups of the
+// 128-channel bank instead of 1536 for all.
 #include "f2_fused.cuh"
 
 #include <stdlib.h>
@@ -438,8 +441,14 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
     }
 
     // ---- tile schedule: E stream [tE0, n) (edge residuals), then M stream [ts, t1) ----
+    // truncated-history lengths of THIS channel group (uniform in the CTA): the plan's lengths belong to
+    // the bank's slowest channel
+    const float wscale = p.chan[P_WSCALE * p.c_pad + item.cblock * kChanPerBlock];
+    const int w_edge_g = group_warmup(p.w_edge, wscale);
+    const int w_casc_g = group_warmup(p.w_casc, wscale);
+    const int w_imag_g = group_warmup(p.w_imag, wscale);
     const int t0 = item.t0, t1 = item.t1;
-    int tE0 = n - p.w_edge;
+    int tE0 = n - w_edge_g;
     tE0 = tE0 > 0 ? (tE0 / kTile) * kTile : 0;
     const bool need_env = WIN || p.env_t != nullptr || p.dec != nullptr || (CN && p.env_cn != nullptr);
     const bool need_imag = need_env && N2 > 2;  // N2 <= 2: the analytic signal is real
@@ -448,11 +457,11 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
     const int nE = (need_imag && !EDGE) ? (n - tE0 + kTile - 1) / kTile : 0;
     const int w_lpf = (p.lpf && need_env) ? p.w_lpf : 0;
     int ts, tenv;
-    if (t0 - w_lpf - p.w_casc <= 0) {
-        ts = need_imag ? -p.w_imag : 0;
+    if (t0 - w_lpf - w_casc_g <= 0) {
+        ts = need_imag ? -w_imag_g : 0;
         tenv = w_lpf > 0 ? 0 : t0;
     } else {
-        ts = t0 - w_lpf - p.w_casc;
+        ts = t0 - w_lpf - w_casc_g;
         tenv = t0 - w_lpf;
     }
     const int nM = (t1 - ts + kTile - 1) / kTile;
