@@ -434,6 +434,9 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         d.N2 = 1 << lg;
         d.log2N2 = lg;
         d.n_dec = n > phase ? (int)((n - phase + step - 1) / step) : 0;
+        d.g_tab = nullptr;   // filled below, on the plan's device
+        d.g_shift = 0;
+        d.pad_ = 0;
         b->frame_off[(size_t)u] = frames;
         wave += n;
         ring += (long long)align_up((size_t)d.N2, f2::kRingAlign);
@@ -544,6 +547,16 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
     b->n_whole = whole / units * cblocks;  // same utterance count, in CTAs
 
     DeviceGuard guard(plan->device);
+    // injection tables shared per ring size (f2_prep.cu): utterance u reads copy s = (-n) mod 4 from (t - n - s) mod N2
+    for (int u = 0; u < n_utts; ++u) {
+        f2::UttDesc& d = b->utts[(size_t)u];
+        int stride = 0;
+        const float* tab = d.n > 0 ? f2::injection_table(d.log2N2, &stride) : nullptr;
+        if (!tab) continue;
+        const int s = (int)((4 - (d.n & 3)) & 3);
+        d.g_tab = tab + (size_t)s * (size_t)stride;
+        d.g_shift = (int)(((long long)d.N2 * 2 - d.n - s) & (d.N2 - 1));
+    }
     cudaError_t e = cudaSuccess;
     if (n_utts > 0) {
         e = cudaMalloc(&b->d_utts, sizeof(f2::UttDesc) * (size_t)n_utts);
@@ -772,6 +785,9 @@ __global__ void rows_desc_kernel(f2::UttDesc* d, long long rows, long long rows_
     u.N2 = 1 << lg;
     u.n_dec = 0;
     u.log2N2 = lg;
+    u.g_tab = nullptr;
+    u.g_shift = 0;
+    u.pad_ = 0;
     d[r] = u;
 }
 }  // namespace

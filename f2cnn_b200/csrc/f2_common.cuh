@@ -56,6 +56,14 @@ struct UttDesc {
     int N2;              // ring length = 2^ceil(log2 n)   (EnvelopeExtraction.py:29)
     int n_dec;           // decimated frames: t = phase + j*step < n
     int log2N2;
+    // Injection kernel G[t] = H[(t - n) mod N2]: H depends on the ring size only.  g_tab != null: one of four
+    // copies of H (shifted by 0..3 samples, so that every tile start is 16-byte aligned for the bulk copies;
+    // each N2 + 256 long, so that a tile never wraps), shared by all utterances of this ring size and
+    // L2-resident; tile of ring position tau starts at g_tab[(tau + g_shift) & (N2 - 1)].  null: a private
+    // table in the workspace (FusedParams::G + ring_off), filled by the pre-pass.
+    const float* g_tab;
+    int g_shift;
+    int pad_;
 };
 
 // One CTA (= one warp) of work: channels [cblock*32, +32) of utterance `utt`, output samples [t0, t1).

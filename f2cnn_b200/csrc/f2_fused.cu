@@ -468,7 +468,8 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
     const int total = nE + nM;
 
     const float2* xz_ring = p.xz + ut.ring_off;
-    const float* g_ring = p.G + ut.ring_off;
+    const float* g_ring = ut.g_tab ? ut.g_tab : p.G + ut.ring_off;
+    const int g_shift = ut.g_tab ? ut.g_shift : 0;
 
     auto tile_time = [&](int kk) { return kk < nE ? tE0 + kk * kTile : ts + (kk - nE) * kTile; };
     auto issue = [&](int kk) {
@@ -476,7 +477,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
         const int tau = tile_time(kk) & mask;
         mbar_expect_tx(&sm.full[b], kTile * 12);
         tma_load_1d(&sm.xz[b][0], xz_ring + tau, kTile * 8, &sm.full[b]);
-        tma_load_1d(&sm.g[b][0], g_ring + tau, kTile * 4, &sm.full[b]);
+        tma_load_1d(&sm.g[b][0], g_ring + ((tau + g_shift) & mask), kTile * 4, &sm.full[b]);
     };
 
     if (big && tid == 0) {
@@ -538,7 +539,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
             for (int i = tid; i < kTile; i += kChanPerBlock) {
                 const int tau = (t + i) & mask;
                 sm.xz[b][i] = xz_ring[tau];
-                sm.g[b][i] = g_ring[tau];
+                sm.g[b][i] = g_ring[(tau + g_shift) & mask];
             }
             __syncwarp();
         }

@@ -18,9 +18,12 @@
 // The same kernels serve the stand-alone envelope path (rows of an arbitrary matrix).
 #include "f2_prep.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 
 namespace f2 {
 
@@ -39,8 +42,27 @@ __global__ void init_twiddle_kernel() {
     }
 }
 
+// four-step twiddles of the cluster kernel's two sizes: g_step14[k1*128 + n2] = exp(-2*pi*i*n2*k1/2^14),
+// g_step15[k1*256 + n2] = exp(-2*pi*i*n2*k1/2^15), k1 < 128 (384 KB, L2-resident; the inverse conjugates)
+__device__ float2 g_step14[1 << 14];
+__device__ float2 g_step15[1 << 15];
+
+__global__ void init_step_twiddle_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double s, c;
+    if (i < (1 << 14)) {
+        sincospi(-2.0 * (double)((i & 127) * (i >> 7)) / (double)(1 << 14), &s, &c);
+        g_step14[i] = make_float2((float)c, (float)s);
+    }
+    if (i < (1 << 15)) {
+        sincospi(-2.0 * (double)((i & 255) * (i >> 8)) / (double)(1 << 15), &s, &c);
+        g_step15[i] = make_float2((float)c, (float)s);
+    }
+}
+
 cudaError_t init_twiddles(cudaStream_t stream) {
     init_twiddle_kernel<<<(1 << (kTwLog - 1)) / 256, 256, 0, stream>>>();
+    init_step_twiddle_kernel<<<(1 << 15) / 256, 256, 0, stream>>>();
     return cudaGetLastError();
 }
 
@@ -53,6 +75,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // packed sample pair (x[2m], x[2m+1]) of an utterance, zero beyond n
 __device__ __forceinline__ float2 load_pair(const void* base, int dtype, long long off, int m, int n) {
@@ -147,6 +170,9 @@ __device__ __forceinline__ void smem_fft(float2* s, int pitch, int logL, int bat
         __syncthreads();
     }
 }
+
+// N2 = 32768 / 65536 are transformed by one cluster kernel (ring_cluster_kernel below)
+__host__ __device__ inline bool ring_cluster_size(int log2N2) { return log2N2 == 15 || log2N2 == 16; }
 
 // legs of 128 / 256 points have a register-pass implementation (see the fast kernels below)
 __host__ __device__ inline bool fast_leg(int l) { return l == 7 || l == 8; }
@@ -419,6 +445,7 @@ __global__ void __launch_bounds__(kFftThreads, SRC_WAVE ? 4 : 3) fft_cols_fast_k
     int l1, l2;
     fft_split(log2M, l1, l2);
     if (log2M <= kTwLog || !fast_leg(l1) || !fast_leg(l2)) return;
+    if (p.cluster && ring_cluster_size(ut.log2N2)) return;  // taken by ring_cluster_kernel
     if (l1 == 7) cols_fast_body<INV, SRC_WAVE, 7>(p, ut, buf, sA, l2);
     else cols_fast_body<INV, SRC_WAVE, 8>(p, ut, buf, sA, l2);
 }
@@ -454,8 +481,56 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fast_kernel(PrepParams p
     int l1, l2;
     fft_split(log2M, l1, l2);
     if (log2M <= kTwLog || !fast_leg(l1) || !fast_leg(l2)) return;
+    if (p.cluster && ring_cluster_size(ut.log2N2)) return;  // taken by ring_cluster_kernel
     if (l2 == 7) rows_fast_body<INV, DST_RING, 7>(p, ut, in_buf, out_buf, sA, l1);
     else rows_fast_body<INV, DST_RING, 8>(p, ut, in_buf, out_buf, sA, l1);
+}
+
+// One pair (Z[k], Z[M-k]) of the packed spectrum -> the pair (W[k], W[M-k]) the inverse packed transform
+// needs (see the derivation above hilbert_mask_kernel); valid for any 0 < k < M, k = M/2 included (a == b).
+__device__ __forceinline__ void hilbert_pair(float2 a, float2 b, int k, float invN, float2& Wk, float2& Wm) {
+    float sn, cs;
+    sincospif(-2.0f * (float)k * invN, &sn, &cs);  // e = exp(-2 pi i k / N)
+    const float2 e = make_float2(cs, sn);
+    // X[k]
+    const float2 sp = make_float2(a.x + b.x, a.y - b.y);  // a + conj(b)
+    const float2 dm = make_float2(a.x - b.x, a.y + b.y);  // a - conj(b)
+    const float2 ed = cmul(e, dm);
+    const float2 Xk = make_float2(0.5f * (sp.x + ed.y), 0.5f * (sp.y - ed.x));  // sp/2 - (i/2) ed
+    // X[M-k] = conj(sp)/2 - (i/2) e2 * (-conj(dm)),  e2 = exp(-2 pi i (M-k)/N) = -conj(e)
+    // => X[M-k] = conj(sp)/2 - (i/2) conj(ed)
+    const float2 Xm = make_float2(0.5f * (sp.x - ed.y), 0.5f * (-sp.y - ed.x));
+    // Y = -i X
+    const float2 Yk = make_float2(Xk.y, -Xk.x);
+    const float2 Ym = make_float2(Xm.y, -Xm.x);
+    // W[k] = (Yk + conj(Ym)) + i conj(e) (Yk - conj(Ym))
+    const float2 s2 = make_float2(Yk.x + Ym.x, Yk.y - Ym.y);
+    const float2 d2 = make_float2(Yk.x - Ym.x, Yk.y + Ym.y);
+    const float2 ce = make_float2(e.x, -e.y);
+    const float2 t2 = cmul(ce, d2);
+    Wk = make_float2((s2.x - t2.y) * invN, (s2.y + t2.x) * invN);
+    // W[M-k] = conj(s2) + i conj(t2)
+    Wm = make_float2((s2.x + t2.y) * invN, (-s2.y + t2.x) * invN);
+}
+
+// H[m], m = (t - n) mod N2: the circular Hilbert kernel h[l] = (2/N2) cot(pi l / N2) at the odd one of m, m-1.
+__device__ __forceinline__ float injection_tap(int m, int N2, float invN) {
+    int l = m;
+    if (!(l & 1)) l = (l - 1) & (N2 - 1);
+    if (l > N2 / 2) l -= N2;  // cot is odd and pi-periodic: keep |l| <= N2/2 for accuracy
+    float sn, cs;
+    sincospif((float)l * invN, &sn, &cs);
+    return 2.0f * invN * cs / sn;
+}
+
+// four shifted copies of H for one ring size: tab[s*(N2+256) + m] = H[(m + s) mod N2]
+__global__ void injection_table_kernel(float* tab, int N2) {
+    const float invN = 1.0f / (float)N2;
+    const int len = N2 + 256;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * len; i += gridDim.x * blockDim.x) {
+        const int s = i / len, m = i - s * len;
+        tab[i] = injection_tap((m + s) & (N2 - 1), N2, invN);
+    }
 }
 
 // ---- untangle the packed real FFT, apply the Hilbert multiplier, tangle for the inverse ----
@@ -468,27 +543,19 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fast_kernel(PrepParams p
 // G[tau] = h[l], l = the odd one of (tau-n) mod N2, (tau-n-1) mod N2,
 // h[l] = (2/N2) cot(pi l / N2): the circular Hilbert kernel for even N2 that matches scipy's
 // one-sided mask.
-__global__ void hilbert_mask_kernel(const UttDesc* utts, float* buf, float* gtab) {
+__global__ void hilbert_mask_kernel(const UttDesc* utts, float* buf, float* gtab, int cluster) {
     const UttDesc ut = utts[blockIdx.x];
     const int N2 = ut.N2;
     const int M = N2 >> 1;
     const float invN = 1.0f / (float)N2;
-    if (gtab) {
+    if (gtab && !ut.g_tab) {
         float* G = gtab + ut.ring_off;
         for (int tau = blockIdx.y * blockDim.x + threadIdx.x; tau < N2; tau += gridDim.y * blockDim.x) {
-            float g = 0.f;
-            if (N2 > 2) {
-                int l = (tau - ut.n) & (N2 - 1);
-                if (!(l & 1)) l = (l - 1) & (N2 - 1);
-                if (l > N2 / 2) l -= N2;  // cot is odd and pi-periodic: keep |l| <= N2/2 for accuracy
-                float sn, cs;
-                sincospif((float)l * invN, &sn, &cs);
-                g = 2.0f * invN * cs / sn;
-            }
-            G[tau] = g;
+            G[tau] = N2 > 2 ? injection_tap((tau - ut.n) & (N2 - 1), N2, invN) : 0.f;
         }
     }
     if (!buf || M < 1) return;
+    if (cluster && ring_cluster_size(ut.log2N2)) return;  // done in shared memory by ring_cluster_kernel
     float2* Z = reinterpret_cast<float2*>(buf + ut.ring_off);
     for (int k = blockIdx.y * blockDim.x + threadIdx.x; k <= M / 2; k += gridDim.y * blockDim.x) {
         if (k == 0) {
@@ -496,28 +563,8 @@ __global__ void hilbert_mask_kernel(const UttDesc* utts, float* buf, float* gtab
             continue;
         }
         const float2 a = Z[k], b = Z[M - k];
-        float sn, cs;
-        sincospif(-2.0f * (float)k * invN, &sn, &cs);  // e = exp(-2 pi i k / N)
-        const float2 e = make_float2(cs, sn);
-        // X[k]
-        const float2 sp = make_float2(a.x + b.x, a.y - b.y);  // a + conj(b)
-        const float2 dm = make_float2(a.x - b.x, a.y + b.y);  // a - conj(b)
-        const float2 ed = cmul(e, dm);
-        const float2 Xk = make_float2(0.5f * (sp.x + ed.y), 0.5f * (sp.y - ed.x));  // sp/2 - (i/2) ed
-        // X[M-k] = conj(sp)/2 - (i/2) e2 * (-conj(dm)),  e2 = exp(-2 pi i (M-k)/N) = -conj(e)
-        // => X[M-k] = conj(sp)/2 - (i/2) conj(ed)
-        const float2 Xm = make_float2(0.5f * (sp.x - ed.y), 0.5f * (-sp.y - ed.x));
-        // Y = -i X
-        const float2 Yk = make_float2(Xk.y, -Xk.x);
-        const float2 Ym = make_float2(Xm.y, -Xm.x);
-        // W[k] = (Yk + conj(Ym)) + i conj(e) (Yk - conj(Ym))
-        const float2 s2 = make_float2(Yk.x + Ym.x, Yk.y - Ym.y);
-        const float2 d2 = make_float2(Yk.x - Ym.x, Yk.y + Ym.y);
-        const float2 ce = make_float2(e.x, -e.y);
-        const float2 t2 = cmul(ce, d2);
-        const float2 Wk = make_float2((s2.x - t2.y) * invN, (s2.y + t2.x) * invN);
-        // W[M-k] = conj(s2) + i conj(t2)
-        const float2 Wm = make_float2((s2.x + t2.y) * invN, (-s2.y + t2.x) * invN);
+        float2 Wk, Wm;
+        hilbert_pair(a, b, k, invN, Wk, Wm);
         Z[k] = Wk;
         if (k != M - k) Z[M - k] = Wm;
     }
@@ -535,6 +582,355 @@ __global__ void plain_ring_kernel(PrepParams p, int only_tiny) {
         const float2 x = load_pair(p.wave, p.wave_dtype, ut.wave_off, m, ut.n);
         ring[m] = make_float4(x.x, 0.f, x.y, 0.f);
     }
+}
+
+
+// =============================================================================================
+// The whole ring transform of an utterance in ONE kernel (N2 = 32768 and 65536, the sizes corpus
+// utterances have): a thread-block cluster keeps the packed spectrum in its distributed shared
+// memory, so HBM sees the wave once (plus one L2-resident re-read) and the (x, xi) ring once --
+// 0.6 MB per utterance where the five-kernel sequence above moves 3 MB through two scratch rings.
+//
+//   M = N2/2 = 128 x M2 packed complex points z[n1*M2 + n2].  CTA `rank` of the CL in the cluster owns
+//   columns [rank*M2/CL, +M2/CL) in the column phases and a mirror-closed set of 128/CL rows in the row
+//   phase (row k1 and row 128-k1 sit in adjacent slots, because the Hilbert step pairs Z[k] with Z[M-k]).
+//   1  columns forward: 128-point FFTs (16 x 8 in registers around one shared exchange), read straight
+//      from the wave; four-step twiddle; every thread then holds 32 values in registers across a
+//      cluster barrier and stores them into the row owners' shared memory (DSMEM): the transposition
+//      never leaves the chip and needs no second buffer.
+//   2  rows: forward M2-point FFT in place (results stay in digit-swapped order), Hilbert pair step,
+//      inverse M2-point FFT in place (the same two register passes, mirrored), inverse twiddle, and
+//      the transposition back through registers + DSMEM.
+//   3  columns inverse: 128-point FFTs, output m = m1*M2 + n2 holds (xi[2m], xi[2m+1]): written with
+//      (x[2m], x[2m+1]) as one float4 of the interleaved ring, 512 contiguous bytes per warp.
+// =============================================================================================
+
+template <int L2, int CL, int T>
+struct RingCl {
+    static constexpr int M1 = 128, M2 = 1 << L2, M = M1 * M2;
+    static constexpr int NC = M2 / CL;   // columns per CTA
+    static constexpr int NR = M1 / CL;   // rows per CTA
+    static constexpr int PC = M1 + 1;    // column pitch (float2): odd, so that column-major tasks spread over the banks
+    static constexpr int PSH = L2 - 4;   // one float2 of padding per 16 (M2 = 256) / 8 (M2 = 128) row elements
+    static constexpr int PR = M2 + (M2 >> PSH) + (L2 == 7 ? 8 : 0);   // row pitch
+    static constexpr int PB3 = NC + 1;   // phase 3 keeps its columns as [k1][b]: the transposing stores of a warp are contiguous
+    static constexpr int kE1 = (NC * PC > NR * PR) ? NC * PC : NR * PR;
+    static constexpr int kElems = kE1 > M1 * PB3 ? kE1 : M1 * PB3;
+    __device__ static __forceinline__ int pad(int q) { return q + (q >> PSH); }
+    // row k1 -> (owner CTA, slot).  f = min(k1, 128-k1); rows f and 128-f go to CTA f % CL, slots 2*(f/CL)
+    // and 2*(f/CL)+1; the two self-mirrored rows 0 and 64 share pair 0 of CTA 0.
+    __device__ static __forceinline__ void owner(int k1, int& cta, int& slot) {
+        const int f = k1 <= M1 / 2 ? k1 : M1 - k1;
+        cta = f % CL;
+        slot = k1 == M1 / 2 ? 1 : 2 * (f / CL) + (k1 > M1 / 2 ? 1 : 0);
+    }
+    __device__ static __forceinline__ int row_of(int cta, int slot) {
+        const int f = (slot >> 1) * CL + cta;
+        if (f == 0) return (slot & 1) ? M1 / 2 : 0;
+        return (slot & 1) ? M1 - f : f;
+    }
+    // position of row frequency k2 after the forward row transform (its second pass leaves k2 = k1' + 16*k2'
+    // at k1'*R2 + k2', R2 = M2/16)
+    __device__ static __forceinline__ int pos(int k2) { return pad((k2 & 15) * (M2 / 16) + (k2 >> 4)); }
+};
+
+template <int L2, int CL, int T>
+__device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const UttDesc& ut, float2* sm) {
+    using S = RingCl<L2, CL, T>;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
+    constexpr int M2 = S::M2, NC = S::NC, NR = S::NR, PC = S::PC, PR = S::PR;
+    constexpr int R2 = M2 / 16;           // second radix of the row transform (16 or 8)
+    const float invN = 0.5f / (float)S::M;
+    // leg twiddles in shared memory behind the data, the index that varies across the threads of a warp
+    // innermost: tw_a[k*8 + n] = w_128^(k*n) (k < 16, n < 8), tw_b[k*16 + n] = w_128^(k*n) (k < 8, n < 16),
+    // tw_r[k*16 + n] = w_256^(k*n) (forward values; the inverse conjugates)
+    float2* tw_a = sm + S::kElems;
+    float2* tw_b = tw_a + 128;
+    float2* tw_r = tw_b + 128;
+    for (int i = tid; i < 128; i += T) {
+        tw_a[i] = leg_twiddle<false>((i >> 3) * (i & 7), 7);
+        tw_b[i] = leg_twiddle<false>((i >> 4) * (i & 15), 7);
+    }
+    if (L2 == 8)
+        for (int i = tid; i < 256; i += T) tw_r[i] = leg_twiddle<false>((i >> 4) * (i & 15), 8);
+    const float2* __restrict__ step = L2 == 7 ? g_step14 : g_step15;   // [k1*M2 + n2]
+    __syncthreads();
+
+    // ---- 1: columns forward ----
+    for (int task = tid; task < NC * 8; task += T) {
+        const int b = task % NC, n2p = task / NC;
+        float2 v[16];
+#pragma unroll
+        for (int n1p = 0; n1p < 16; ++n1p)
+            v[n1p] = load_pair(p.wave, p.wave_dtype, ut.wave_off, (n1p * 8 + n2p) * M2 + rank * NC + b, ut.n);
+        fft16<false>(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int k1p = out16(r);
+            sm[b * PC + k1p * 8 + n2p] = cmul(v[r], tw_a[k1p * 8 + n2p]);
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int NT = NC * 16 / T;
+        static_assert(NT * T == NC * 16, "column pass 2 tasks must divide evenly");
+        float2 h[NT][8];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int task = tid + i * T;
+            const int b = task % NC, k1p = task / NC;
+#pragma unroll
+            for (int n2p = 0; n2p < 8; ++n2p) h[i][n2p] = sm[b * PC + k1p * 8 + n2p];
+            fft8<false>(h[i]);
+            const int n2 = rank * NC + b;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int k1 = k1p + 16 * out8(r);
+                h[i][r] = cmul(h[i][r], __ldg(step + k1 * M2 + n2));
+            }
+        }
+        cluster.sync();   // every CTA has its column data in registers: the buffers may be overwritten
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int task = tid + i * T;
+            const int b = task % NC, k1p = task / NC;
+            const int n2 = rank * NC + b;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                int cta, slot;
+                S::owner(k1p + 16 * out8(r), cta, slot);
+                float2* dst = cluster.map_shared_rank(sm, cta);
+                dst[slot * PR + S::pad(n2)] = h[i][r];
+            }
+        }
+        cluster.sync();
+    }
+
+    // ---- 2a: rows forward, in place ----
+    for (int task = tid; task < NR * R2; task += T) {
+        const int n2p = task % R2, slot = task / R2;
+        float2* row = sm + slot * PR;
+        float2 v[16];
+#pragma unroll
+        for (int n1p = 0; n1p < 16; ++n1p) v[n1p] = row[S::pad(n1p * R2 + n2p)];
+        fft16<false>(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int k1p = out16(r);
+            row[S::pad(k1p * R2 + n2p)] = cmul(v[r], L2 == 8 ? tw_r[k1p * 16 + n2p] : tw_a[k1p * 8 + n2p]);
+        }
+    }
+    __syncthreads();
+    for (int task = tid; task < NR * 16; task += T) {
+        const int k1p = task % 16, slot = task / 16;
+        float2* row = sm + slot * PR;
+        if (R2 == 16) {
+            float2 v[16];
+#pragma unroll
+            for (int n2p = 0; n2p < 16; ++n2p) v[n2p] = row[S::pad(k1p * 16 + n2p)];
+            fft16<false>(v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) row[S::pad(k1p * 16 + out16(r))] = v[r];   // k2 = k1p + 16*out16(r)
+        } else {
+            float2 v[8];
+#pragma unroll
+            for (int n2p = 0; n2p < 8; ++n2p) v[n2p] = row[S::pad(k1p * 8 + n2p)];
+            fft8<false>(v);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) row[S::pad(k1p * 8 + out8(r))] = v[r];
+        }
+    }
+    __syncthreads();
+
+    // ---- 2b: Hilbert multiplier on the pairs (k, M-k), k = k1 + 128*k2 ----
+    for (int task = tid; task < (NR / 2) * M2; task += T) {
+        const int k2 = task % M2, j = task / M2;
+        if (rank == 0 && j == 0) continue;   // rows 0 and 64: below
+        const int k1 = S::row_of(rank, 2 * j);
+        float2* pa = sm + (2 * j) * PR + S::pos(k2);
+        float2* pb = sm + (2 * j + 1) * PR + S::pos(M2 - 1 - k2);
+        float2 Wk, Wm;
+        hilbert_pair(*pa, *pb, k1 + S::M1 * k2, invN, Wk, Wm);
+        *pa = Wk;
+        *pb = Wm;
+    }
+    if (rank == 0) {
+        for (int task = tid; task < M2 + 1; task += T) {
+            if (task <= M2 / 2) {   // row 0: k = 128*k2 pairs with 128*(M2-k2)
+                float2* pa = sm + S::pos(task);
+                if (task == 0) {
+                    *pa = make_float2(0.f, 0.f);
+                } else {
+                    float2* pb = sm + S::pos(M2 - task);
+                    float2 Wk, Wm;
+                    hilbert_pair(*pa, *pb, S::M1 * task, invN, Wk, Wm);
+                    *pa = Wk;
+                    if (task != M2 / 2) *pb = Wm;
+                }
+            } else {                // row 64: k = 64 + 128*k2 pairs with 64 + 128*(M2-1-k2)
+                const int k2 = task - (M2 / 2 + 1);
+                float2* pa = sm + PR + S::pos(k2);
+                float2* pb = sm + PR + S::pos(M2 - 1 - k2);
+                float2 Wk, Wm;
+                hilbert_pair(*pa, *pb, S::M1 / 2 + S::M1 * k2, invN, Wk, Wm);
+                *pa = Wk;
+                *pb = Wm;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 2c: rows inverse, in place; natural index i sits at pos(i) ----
+    if (R2 == 16) {
+        for (int task = tid; task < NR * 16; task += T) {
+            const int n2p = task % 16, slot = task / 16;
+            float2* row = sm + slot * PR;
+            float2 v[16];
+#pragma unroll
+            for (int n1p = 0; n1p < 16; ++n1p) v[n1p] = row[S::pad(n2p * 16 + n1p)];   // i = n1p*16 + n2p
+            fft16<true>(v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int k1p = out16(r);
+                row[S::pad(n2p * 16 + k1p)] = cmul(v[r], cconj(tw_r[k1p * 16 + n2p]));
+            }
+        }
+    } else {
+        // 128 = 8 x 16: 8-point transforms over n1 (i = n1*16 + n2 at pos = n2*8 + n1), then 16-point over n2
+        for (int task = tid; task < NR * 16; task += T) {
+            const int n2p = task % 16, slot = task / 16;
+            float2* row = sm + slot * PR;
+            float2 v[8];
+#pragma unroll
+            for (int n1p = 0; n1p < 8; ++n1p) v[n1p] = row[S::pad(n2p * 8 + n1p)];
+            fft8<true>(v);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int k1p = out8(r);
+                row[S::pad(n2p * 8 + k1p)] = cmul(v[r], cconj(tw_b[k1p * 16 + n2p]));
+            }
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int R1 = M2 / 16;   // first radix of the inverse row transform: 16 (M2 = 256) or 8
+        constexpr int NT = NR * R1 / T > 0 ? NR * R1 / T : 1;
+        static_assert(NR * R1 % T == 0 || NR * R1 < T, "row pass 2 tasks");
+        float2 g[NT][16];
+        bool live[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int task = tid + i * T;
+            live[i] = task < NR * R1;
+            const int k1p = task % R1, slot = live[i] ? task / R1 : 0;
+            const float2* row = sm + slot * PR;
+#pragma unroll
+            for (int n2p = 0; n2p < 16; ++n2p) g[i][n2p] = row[S::pad(n2p * R1 + k1p)];
+            fft16<true>(g[i]);
+            const int k1 = S::row_of(rank, slot);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int m2 = k1p + R1 * out16(r);
+                g[i][r] = cmul(g[i][r], cconj(__ldg(step + k1 * M2 + m2)));
+            }
+        }
+        cluster.sync();
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int task = tid + i * T;
+            const int k1p = task % R1, slot = live[i] ? task / R1 : 0;
+            const int k1 = S::row_of(rank, slot);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int m2 = k1p + R1 * out16(r);
+                float2* dst = cluster.map_shared_rank(sm, m2 / NC);
+                if (live[i]) dst[k1 * S::PB3 + (m2 % NC)] = g[i][r];
+            }
+        }
+        cluster.sync();
+    }
+
+    // ---- 3: columns inverse (data as [k1][b]), ring store ----
+    for (int task = tid; task < NC * 8; task += T) {
+        const int b = task % NC, n2p = task / NC;
+        float2* col = sm + b;
+        float2 v[16];
+#pragma unroll
+        for (int n1p = 0; n1p < 16; ++n1p) v[n1p] = col[(n1p * 8 + n2p) * S::PB3];
+        fft16<true>(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int k1p = out16(r);
+            col[(k1p * 8 + n2p) * S::PB3] = cmul(v[r], cconj(tw_a[k1p * 8 + n2p]));
+        }
+    }
+    __syncthreads();
+    float4* ring = reinterpret_cast<float4*>(p.xz + ut.ring_off);
+    for (int task = tid; task < NC * 16; task += T) {
+        const int b = task % NC, k1p = task / NC;
+        const float2* col = sm + b;
+        float2 v[8], x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)   // the wave again (L2): issued before the transform that hides their latency
+            x[r] = load_pair(p.wave, p.wave_dtype, ut.wave_off, (k1p + 16 * out8(r)) * M2 + rank * NC + b, ut.n);
+#pragma unroll
+        for (int n2p = 0; n2p < 8; ++n2p) v[n2p] = col[(k1p * 8 + n2p) * S::PB3];
+        fft8<true>(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            ring[(k1p + 16 * out8(r)) * M2 + rank * NC + b] = make_float4(x[r].x, v[r].x, x[r].y, v[r].y);
+    }
+}
+
+#ifndef F2_RING_CL
+#define F2_RING_CL 4
+#endif
+#ifndef F2_RING_CTAS
+#define F2_RING_CTAS 2
+#endif
+constexpr int kRingCl = F2_RING_CL;   // CTAs per cluster
+constexpr int kRingClThreads = 512;
+constexpr int kRingClSmem =
+    (RingCl<8, kRingCl, kRingClThreads>::kElems > RingCl<7, kRingCl, kRingClThreads>::kElems
+         ? RingCl<8, kRingCl, kRingClThreads>::kElems
+         : RingCl<7, kRingCl, kRingClThreads>::kElems) * (int)sizeof(float2) + 512 * (int)sizeof(float2);
+
+__global__ void __cluster_dims__(kRingCl, 1, 1) __launch_bounds__(kRingClThreads, F2_RING_CTAS) ring_cluster_kernel(PrepParams p) {
+    extern __shared__ float2 s_fft[];
+    const UttDesc ut = p.utts[blockIdx.x / kRingCl];
+    if (ut.log2N2 == 16) ring_cluster_body<8, kRingCl, kRingClThreads>(p, ut, s_fft);
+    else if (ut.log2N2 == 15) ring_cluster_body<7, kRingCl, kRingClThreads>(p, ut, s_fft);
+}
+
+// One injection table per (device, ring size), built on first use and kept for the life of the process
+// (16 bytes per ring sample: 1 MB for N2 = 65536); immutable afterwards, so every stream may read it.
+const float* injection_table(int log2N2, int* stride) {
+    if (log2N2 < kGTabMinLog || log2N2 > kGTabMaxLog) return nullptr;
+    static std::mutex mu;
+    static float* cache[64][kGTabMaxLog + 1] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return nullptr;
+    const int N2 = 1 << log2N2;
+    if (stride) *stride = N2 + 256;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cache[dev][log2N2]) {
+        float* t = nullptr;
+        if (cudaMalloc(&t, sizeof(float) * 4 * (size_t)(N2 + 256)) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;   // the caller falls back to per-utterance tables
+        }
+        injection_table_kernel<<<std::min(1024, (4 * (N2 + 256) + 255) / 256), 256>>>(t, N2);
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(t);
+            return nullptr;
+        }
+        cache[dev][log2N2] = t;
+    }
+    return cache[dev][log2N2];
 }
 
 static int max_blocks(const HostPrepInfo& h, bool cols) {
@@ -560,8 +956,12 @@ static int max_blocks(const HostPrepInfo& h, bool cols) {
     return best;
 }
 
-cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t stream) {
+cudaError_t launch_prep(const PrepParams& p_in, const HostPrepInfo& h, cudaStream_t stream) {
     if (h.n_utts <= 0) return cudaSuccess;
+    // development knob: F2CNN_B200_RING_CLUSTER=0 sends every size through the multi-pass kernels
+    static const bool cluster_on = [] { const char* v = getenv("F2CNN_B200_RING_CLUSTER"); return !(v && v[0] == '0'); }();
+    PrepParams p = p_in;
+    p.cluster = cluster_on && p.hilbert && h.min_log2N2 <= 16 && h.max_log2N2 >= 15;
     if (h.max_log2N2 - 1 > 2 * kTwLog) return cudaErrorInvalidValue;
     // per device: the attribute belongs to the current device's copy of the function
     static bool attr_done[64] = {false};
@@ -575,6 +975,7 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
         cudaFuncSetAttribute(fft_rows_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_rows_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_cols_fast_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(ring_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingClSmem);
         if (dev < 64) attr_done[dev] = true;
     }
     const int maxN2 = 1 << h.max_log2N2;
@@ -583,7 +984,7 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
     const dim3 g_ew(h.n_utts, ew_blocks);
     if (!p.hilbert || h.max_log2N2 < 2) {
         plain_ring_kernel<<<g_ew, 256, 0, stream>>>(p, 0);
-        if (p.G) hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, nullptr, p.G);  // N2 <= 2: G = 0
+        if (p.G) hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, nullptr, p.G, 0);  // N2 <= 2: G = 0
         return cudaGetLastError();
     }
     const bool two = (h.max_log2N2 - 1) > kTwLog;
@@ -593,6 +994,7 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
     int fast_blocks = 1;
     for (int lg = h.min_log2N2; lg <= h.max_log2N2; ++lg) {
         if (lg - 1 <= kTwLog) continue;
+        if (p.cluster && ring_cluster_size(lg)) continue;
         int l1, l2;
         fft_split(lg - 1, l1, l2);
         if (fast_leg(l1) && fast_leg(l2)) {
@@ -607,6 +1009,9 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
     const dim3 g_rows(h.n_utts, max_blocks(h, false));
     float* A = p.bufA;
     float* B = p.bufB;
+    // whole transform in one cluster kernel for the corpus sizes (its utterances are skipped by everything below
+    // except the G table)
+    if (p.cluster) ring_cluster_kernel<<<kRingCl * h.n_utts, kRingClThreads, kRingClSmem, stream>>>(p);
     // forward
     if (fast) fft_cols_fast_kernel<false, true><<<g_fast, kFftThreads, 0, stream>>>(p, A);
     if (fast) fft_rows_fast_kernel<false, false><<<g_fast, kFftThreads, 0, stream>>>(p, A, B);
@@ -614,7 +1019,7 @@ cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t
     if (two && slow2) fft_rows_kernel<false, false, false><<<g_rows, kFftThreads, smem, stream>>>(p, A, B);
     if (one) fft_rows_kernel<false, true, false><<<g_rows, kFftThreads, smem, stream>>>(p, nullptr, B);
     // Hilbert multiplier in place on B; the injection kernel goes to A (free from here on)
-    hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, B, p.G);
+    hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, B, p.G, p.cluster);
     // inverse, last pass writes the (x, xi) ring
     if (fast) fft_cols_fast_kernel<true, false><<<g_fast, kFftThreads, 0, stream>>>(p, B);
     if (fast) fft_rows_fast_kernel<true, true><<<g_fast, kFftThreads, 0, stream>>>(p, B, nullptr);

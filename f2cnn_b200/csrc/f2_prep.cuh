@@ -19,6 +19,7 @@ struct PrepParams {
     float* G;          // out: injection kernel rings; must alias bufA (free once the forward
                        // transform is done) or be null (plain Hilbert, no table)
     int hilbert;       // 0: filterbank-only run, skip the FFTs and leave xi = 0
+    int cluster;       // set by launch_prep: N2 = 32768 / 65536 go through ring_cluster_kernel
 };
 
 struct HostPrepInfo {
@@ -27,6 +28,10 @@ struct HostPrepInfo {
     int max_log2N2;
 };
 
+constexpr int kGTabMinLog = 8, kGTabMaxLog = 20;   // ring sizes that share one injection table per device
+// device pointer to the four shifted copies (stride floats apart) of the table for N2 = 2^log2N2 on the
+// current device, or null (size out of range / out of memory: use per-utterance tables)
+const float* injection_table(int log2N2, int* stride);
 cudaError_t init_twiddles(cudaStream_t stream);
 cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t stream);
 
