@@ -239,6 +239,7 @@ struct f2_batch {
     long long total_samples = 0, total_frames = 0, total_ring = 0;
     int max_n = 0;
     int min_log2 = 0, max_log2 = 0;
+    int private_g = 0;  // utterances without a shared injection table
 };
 
 extern "C" {
@@ -552,7 +553,10 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
         f2::UttDesc& d = b->utts[(size_t)u];
         int stride = 0;
         const float* tab = d.n > 0 ? f2::injection_table(d.log2N2, &stride) : nullptr;
-        if (!tab) continue;
+        if (!tab) {
+            if (d.n > 0) b->private_g += 1;
+            continue;
+        }
         const int s = (int)((4 - (d.n & 3)) & 3);
         d.g_tab = tab + (size_t)s * (size_t)stride;
         d.g_shift = (int)(((long long)d.N2 * 2 - d.n - s) & (d.N2 - 1));
@@ -694,6 +698,7 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
     hp.n_utts = b->n_utts;
     hp.min_log2N2 = b->min_log2;
     hp.max_log2N2 = b->max_log2;
+    hp.private_g = b->private_g;
     F2_CUDA(f2::launch_prep(pp, hp, stream));
 
     f2::FusedParams fp;
@@ -849,6 +854,7 @@ int f2_rows_op(f2_plan* plan, const void* matrix, int dtype, int64_t rows, int64
     f2::HostPrepInfo hp;
     hp.n_utts = (int)rows;
     hp.min_log2N2 = hp.max_log2N2 = r.lg;
+    hp.private_g = 0;
     F2_CUDA(f2::launch_prep(pp, hp, stream));
     F2_CUDA(f2::launch_rows_envelope(d_rows, (int)r.rows_pad, xz, op, lpf ? 1 : 0, (float)(-a1), (float)b0, out,
                                      out_dtype, stream));

@@ -285,14 +285,22 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(PrepParams p, con
 //   pass 2: thread (fft b, k1) reads A[b][k1][n2], n2 < R2, runs an R2-point FFT in registers:
 //           X[k1 + 16*k2].
 // =============================================================================================
+// complex add / subtract as ONE packed instruction (FADD2; FFMA2 with -1): same IEEE results as the scalar pairs
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+
 template <bool INV>
 __device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
-    const float2 j13 = INV ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);  // -/+ i * d13
-    a0 = cadd(s02, s13);
-    a2 = csub(s02, s13);
-    a1 = cadd(d02, j13);
-    a3 = csub(d02, j13);
+    const float2 s02 = padd(a0, a2), d02 = psub(a0, a2), s13 = padd(a1, a3), d13 = psub(a1, a3);
+    a0 = padd(s02, s13);
+    a2 = psub(s02, s13);
+    if (INV) {   // a1 = d02 + i*d13, a3 = d02 - i*d13
+        a1 = make_float2(d02.x - d13.y, d02.y + d13.x);
+        a3 = make_float2(d02.x + d13.y, d02.y - d13.x);
+    } else {
+        a1 = make_float2(d02.x + d13.y, d02.y - d13.x);
+        a3 = make_float2(d02.x - d13.y, d02.y + d13.x);
+    }
 }
 
 template <bool INV>
@@ -893,6 +901,7 @@ __device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const Utt
 #endif
 constexpr int kRingCl = F2_RING_CL;   // CTAs per cluster
 constexpr int kRingClThreads = 512;
+constexpr int kRingAhead = 148 * F2_RING_CTAS / F2_RING_CL;   // clusters resident at a time
 constexpr int kRingClSmem =
     (RingCl<8, kRingCl, kRingClThreads>::kElems > RingCl<7, kRingCl, kRingClThreads>::kElems
          ? RingCl<8, kRingCl, kRingClThreads>::kElems
@@ -900,7 +909,22 @@ constexpr int kRingClSmem =
 
 __global__ void __cluster_dims__(kRingCl, 1, 1) __launch_bounds__(kRingClThreads, F2_RING_CTAS) ring_cluster_kernel(PrepParams p) {
     extern __shared__ float2 s_fft[];
-    const UttDesc ut = p.utts[blockIdx.x / kRingCl];
+    const int u = blockIdx.x / kRingCl, n_utts = gridDim.x / kRingCl;
+    const UttDesc ut = p.utts[u];
+    {
+        // The first thing a cluster does is wait for its wave from HBM with nothing to overlap it with: pull the
+        // wave of the cluster that will run here one generation later into L2 now (one 128-byte line per thread).
+        const int ahead = u + kRingAhead;
+        if (ahead < n_utts) {
+            const UttDesc nx = p.utts[ahead];
+            const int esz = p.wave_dtype == F2_DT_I16 ? 2 : (p.wave_dtype == F2_DT_F32 ? 4 : 8);
+            const char* base = reinterpret_cast<const char*>(p.wave) + nx.wave_off * esz;
+            const long long bytes = (long long)nx.n * esz;
+            for (long long o = ((long long)(blockIdx.x % kRingCl) * kRingClThreads + threadIdx.x) * 128; o < bytes;
+                 o += (long long)kRingCl * kRingClThreads * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+        }
+    }
     if (ut.log2N2 == 16) ring_cluster_body<8, kRingCl, kRingClThreads>(p, ut, s_fft);
     else if (ut.log2N2 == 15) ring_cluster_body<7, kRingCl, kRingClThreads>(p, ut, s_fft);
 }
@@ -1019,7 +1043,8 @@ cudaError_t launch_prep(const PrepParams& p_in, const HostPrepInfo& h, cudaStrea
     if (two && slow2) fft_rows_kernel<false, false, false><<<g_rows, kFftThreads, smem, stream>>>(p, A, B);
     if (one) fft_rows_kernel<false, true, false><<<g_rows, kFftThreads, smem, stream>>>(p, nullptr, B);
     // Hilbert multiplier in place on B; the injection kernel goes to A (free from here on)
-    hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, B, p.G, p.cluster);
+    const bool all_cluster = p.cluster && h.min_log2N2 >= 15 && h.max_log2N2 <= 16;
+    if (!all_cluster || (p.G && h.private_g > 0)) hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, B, p.G, p.cluster);
     // inverse, last pass writes the (x, xi) ring
     if (fast) fft_cols_fast_kernel<true, false><<<g_fast, kFftThreads, 0, stream>>>(p, B);
     if (fast) fft_rows_fast_kernel<true, true><<<g_fast, kFftThreads, 0, stream>>>(p, B, nullptr);

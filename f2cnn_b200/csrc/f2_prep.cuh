@@ -26,6 +26,7 @@ struct HostPrepInfo {
     int n_utts;
     int min_log2N2;
     int max_log2N2;
+    int private_g;   // utterances whose injection table lives in the workspace (UttDesc::g_tab == null)
 };
 
 constexpr int kGTabMinLog = 8, kGTabMaxLog = 20;   // ring sizes that share one injection table per device
