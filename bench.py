@@ -437,8 +437,8 @@ def main():
                "ms_per_step": ms_e2e, "first_call_ms": cold_ms, "fresh_output_ms": fresh_ms, "timer": "host wall clock "
                "around the call (it returns when the last row is placed), max over ranks",
                "path": "api.features_to_windows((pinned int16 waves, lengths), coefs, centres, LPF=True, 50, out=..., "
-                       "counts=...%s): cached engine.WindowPipeline, %s sub-batches, H2D / compute / D2H of the decimated "
-                       "frames on three streams, rows placed by %s host threads per rank" %
+                       "counts=...%s): cached engine.WindowPipeline, %s sub-batches, uploads on one stream, kernels on two, the "
+                       "fused kernel stores its decimated frames into pinned host memory, rows placed by %s host threads per rank" %
                        ("" if world == 1 else ", shard=(rank, world)", pipe_subs[0] if pipe_subs else "?",
                         pipe_subs[1] if pipe_subs else "?"),
                "output": backing, "equals_single_gpu_result": verified, "frames_per_rank": my_frames}

@@ -5,6 +5,7 @@ computation of the hot path happens in libf2cnn_b200.so.  Nothing here falls bac
 numpy/scipy/torch math: without the library or a CUDA device the calls raise."""
 import ctypes
 import hashlib
+import os
 import threading
 
 import numpy as np
@@ -195,8 +196,9 @@ class Batch:
                 "env_t": (C * self.total_samples, (torch.float32,)), "dec": (C * self.total_frames, (torch.float32,))}
         for key, (numel, dts) in want.items():
             t = res.get(key)
+            mapped = key == "dec" and t is not None and t.device.type == "cpu" and t.is_pinned()   # kernel stores over PCIe
             if t is not None and (t.numel() < numel or t.dtype not in dts or not t.is_contiguous() or
-                                  t.device != plan.device):
+                                  (t.device != plan.device and not mapped)):
                 raise ValueError("preallocated %r: need >= %d contiguous elements of %s on %s" % (key, numel, dts, plan.device))
         if gfb is not None and "gfb" not in res:
             res["gfb"] = torch.empty(C * self.total_samples, dtype=gfb, device=plan.device)
@@ -363,10 +365,13 @@ class WindowPipeline:
     consecutive decimated frames -- so the DECIMATED FRAMES travel over PCIe (0.68 GB for the
     4620-utterance corpus instead of 7.5 GB) and the rows are placed on the host by the worker pool
     of f2_host.cpp.  The utterances are cut into sub-batches: the waves of all of them are queued
-    on an upload stream at the start, sub-batch i is filtered on the compute stream while the
-    frames of sub-batch i-1 travel on a download stream, and each download is followed, in stream
-    order, by the host placement of its rows (cudaLaunchHostFunc -> thread pool), so the host
-    never waits between sub-batches.  Consecutive sub-batches run on two alternating compute
+    on an upload stream at the start, sub-batch i is filtered on a compute stream, and the fused
+    kernel stores its decimated frames STRAIGHT INTO THE PINNED HOST BUFFER (posted PCIe writes
+    spread over the kernel's run time: 16 GB/s on average; a device buffer plus one D2H copy per
+    sub-batch arrives in bursts that fight the placement threads for the host's DRAM and was 3 ms
+    slower per corpus -- `zero_copy = False` / F2CNN_B200_ZERO_COPY_FRAMES=0 brings it back).  The
+    end of each sub-batch's kernels is followed, in stream order, by the host placement of its rows
+    (cudaLaunchHostFunc -> thread pool), so the host never waits between sub-batches.  Consecutive sub-batches run on two alternating compute
     streams (each with its own ring workspace), so the tail of one launch overlaps the head of the
     next.
 
@@ -394,6 +399,8 @@ class WindowPipeline:
         # sub-batches of total/n_sub samples, except that the first few grow from an eighth of that (nothing
         # can be placed before the first sub-batch is uploaded, filtered and downloaded) and the last few
         # shrink to a quarter (the rows of the last sub-batch are placed after the GPU has gone idle)
+        if n_sub is None and os.environ.get("F2CNN_B200_NSUB"):
+            n_sub = int(os.environ["F2CNN_B200_NSUB"])   # development knob
         if n_sub is None:
             # a sub-batch should still fill the device: 592 utterances x 4 channel groups = one wave of CTAs
             n_sub = min(U // 576, 8)
@@ -446,6 +453,9 @@ class WindowPipeline:
             self._ev_out = [torch.cuda.Event(enable_timing=True) for _ in self.subs]
             self._ev_start = torch.cuda.Event(enable_timing=True)
             self._ev_end = torch.cuda.Event(blocking=True)
+        # True: the fused kernel stores the decimated frames straight into the pinned host buffer (posted PCIe
+        # writes spread over the kernel's run time) instead of a device buffer + one D2H copy per sub-batch
+        self.zero_copy = os.environ.get("F2CNN_B200_ZERO_COPY_FRAMES", "1") == "1"
         self.timing = False     # True: run() synchronises first and keeps a timeline (see timeline())
         self._t0 = None
         self.placer = placer if placer is not None else Placer()
@@ -530,7 +540,7 @@ class WindowPipeline:
                     self._ev_in[i].record(self._s_in)
             comp = self._s_comp[i & 1]
             comp.wait_event(self._ev_in[i])
-            dec = self._dec_dev[sub["f0"]:sub["f1"]]
+            dec = (self._dec_host if self.zero_copy else self._dec_dev)[sub["f0"]:sub["f1"]]
             sub["batch"].run(self._wave_dev[sub["s0"]:sub["s1"]], lpf=self.lpf, cutoff=self.cutoff, out={"dec": dec},
                              stream=comp)
             self._ev_done[i].record(comp)
@@ -543,7 +553,7 @@ class WindowPipeline:
         with torch.cuda.stream(self._s_out):
             for i, sub in enumerate(self.subs):
                 self._s_out.wait_event(self._ev_done[i])
-                if sub["f1"] > sub["f0"]:
+                if sub["f1"] > sub["f0"] and not self.zero_copy:
                     self._dec_host[sub["f0"]:sub["f1"]].copy_(self._dec_dev[sub["f0"]:sub["f1"]], non_blocking=True)
                 self._ev_out[i].record(self._s_out)
                 if per_sub[i].shape[0]:
