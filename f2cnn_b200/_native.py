@@ -111,6 +111,8 @@ SIGNATURES = {
     "f2_placer_trace": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "f2_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "f2_host_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "f2_host_pin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "f2_host_unpin": (ctypes.c_int, [ctypes.c_void_p]),
     "f2_cnn_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "f2_cnn_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "f2_cnn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int64]),

@@ -211,6 +211,11 @@ F2_API int64_t f2_placer_trace(f2_placer* placer, double* out, int64_t max_jobs,
  * costs two million page faults on its first write). */
 F2_API int f2_host_alloc(size_t bytes, void** out);
 F2_API int f2_host_free(void* ptr, size_t bytes);
+/* Page-lock a block from f2_host_alloc for the current device and make it addressable from kernels under
+ * its host pointer (cudaHostRegister, portable | mapped, after faulting the pages in); f2_host_unpin before
+ * f2_host_free.  F2_ERR_UNSUPPORTED where device and host pointer of registered memory differ. */
+F2_API int f2_host_pin(void* ptr, size_t bytes);
+F2_API int f2_host_unpin(void* ptr);
 
 /* ---- label generation ---------------------------------------
  * Least-squares line through the `dots` = 2*RADIUS+1 formant frames around each timepoint and the
