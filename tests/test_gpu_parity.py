@@ -595,3 +595,72 @@ def test_corpus_pipeline_input_forms_out_argument_and_fallthrough(gpu, monkeypat
         bad = [t.copy() for t in tps]
         bad[30] = np.concatenate([bad[30], [int(lengths[30]) - 100]])
         api.features_to_windows(waves, co, bad, True, 50)
+
+
+def test_one_kernel_ring_transform_sizes(gpu, oracle):
+    """The cluster kernel that transforms rings of 32768 and 65536 samples (every corpus utterance) in
+    distributed shared memory: Im(paddedHilbert) of rows on both sides of its size range against the float64
+    oracle (EnvelopeExtraction.py:20-36), including the sizes next to it that take the multi-pass kernels."""
+    api, engine, filters, torch = gpu
+    rng = np.random.default_rng(21)
+    for n in (16384, 16385, 20001, 32768, 32769, 47001, 65535, 65536, 65537):
+        m = rng.normal(0.0, 3000.0, (3, n))
+        got = api.hilbert_imag_rows(m)
+        for r in range(3):
+            want = oracle.padded_hilbert(m[r]).imag
+            assert np.max(np.abs(got[r] - want)) <= 1e-5 * np.sqrt(np.mean(want ** 2)), n
+
+
+def test_ring_transform_is_independent_of_the_batch_and_of_wave_alignment(gpu):
+    """An utterance gives the same bits alone, in a batch of hundreds (many clusters in flight, odd and even
+    offsets into the int16 buffer: the cluster kernel's aligned and unaligned pair loads) and on a second run."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = coefs128()
+    plan = engine.plan_for(co)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(16385, 65537, size=300).astype(np.int64)
+    lens[::7] += 1 - (lens[::7] & 1)          # some odd lengths: the next utterance starts at an odd sample
+    waves = [synth.white_noise_i16(int(n), seed=100 + i) for i, n in enumerate(lens)]
+    flat = torch.from_numpy(np.concatenate(waves)).cuda()
+    batch = plan.batch(lens, target_items=1)
+    first = batch.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
+    again = batch.run(flat, lpf=True, cutoff=50, dec=True)["dec"].cpu().numpy()
+    assert np.array_equal(first, again)
+    for u in (0, 1, 6, 7, 8, 150, 299):
+        single = plan.batch([int(lens[u])], target_items=1).run(torch.from_numpy(waves[u]).cuda(), lpf=True, cutoff=50,
+                                                                 dec=True)["dec"].cpu().numpy()
+        assert np.array_equal(single, first[batch.frame_offsets[u]:batch.frame_offsets[u + 1]]), u
+
+
+def test_shared_injection_tables_equal_private_ones(gpu, oracle):
+    """Ring sizes 2^8..2^20 read the injection kernel G from one table per size (four shifted copies);
+    smaller and larger rings tabulate it per utterance.  Lengths on both sides of both limits, every
+    residue of n mod 4 (which copy is read), against the oracle."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = coefs128()
+    for n in (120, 128, 129, 255, 256, 257, 1021, 1022, 1023, 1024, 4097):
+        w = synth.white_noise_i16(n, seed=n)
+        _, env = api.filterbank_envelope(w, co, False, 100, with_gfb=True)
+        _, eo, _ = oracle.utterance(w, co, False, 100)
+        tol = TOL if n >= 255 else 2e-3   # rings shorter than a tile: DESIGN.md section 2 (ii)
+        assert rel_err(env, eo).max() <= tol, n
+
+
+def test_pinned_block_is_addressable_from_kernels(gpu):
+    """engine._pinned_empty: huge-page mapping registered with CUDA (f2_host_pin).  The fused kernel stores
+    decimated frames straight into it; the result equals the device-buffer result."""
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    co = coefs128()
+    plan = engine.plan_for(co)
+    w = synth.white_noise_i16(40000, seed=3)
+    batch = plan.batch([40000], target_items=1)
+    host = engine._pinned_empty(batch.total_frames * 128, torch.float32).view(-1, 128)
+    assert host.is_pinned()
+    host.zero_()
+    dev = batch.run(torch.from_numpy(w).cuda(), lpf=True, cutoff=50, dec=True)["dec"]
+    batch.run(torch.from_numpy(w).cuda(), lpf=True, cutoff=50, out={"dec": host})
+    torch.cuda.synchronize()
+    assert np.array_equal(host.numpy(), dev.cpu().numpy())
