@@ -76,6 +76,23 @@ def filterbank_envelope(wave, coefs, LPF=False, CUTOFF=100, with_gfb=False, dtyp
     return env
 
 
+def gammatonegram(wave, coefs, hop, LPF=False, CUTOFF=100, dtype=np.float64):
+    """Every `hop`-th sample of the envelope of `filterbank_envelope` -- (C, ceil(n / hop)), the samples at
+    t = 0, hop, 2*hop, ... -- stored by the fused kernel itself: what a plot of a whole file needs
+    (scripts/plotting/PlottingProcessing.py:101-109 takes the full-rate matrix for it)."""
+    w = _as_wave(wave)
+    coefs = np.asarray(coefs, dtype=np.float64)
+    plan = engine.plan_for(coefs)
+    n, hop = int(w.shape[0]), int(hop)
+    if hop < 1:
+        raise ValueError("hop must be >= 1")
+    if n == 0:
+        return np.zeros((plan.n_channels, 0), dtype=dtype)
+    batch = plan.batch([n], step=hop, phase=0)
+    dec = batch.run(_to_device(w, plan.device), lpf=LPF, cutoff=CUTOFF, dec=True)["dec"]
+    return np.ascontiguousarray(_to_host(dec).T.astype(dtype, copy=False))
+
+
 def extract_envelope_from_matrix(matrix, LPF=False, CUTOFF=100, dtype=np.float64):
     """scripts/processing/EnvelopeExtraction.py:51-67 on an arbitrary (rows, n) matrix:
     abs(paddedHilbert(row)) then lowPassFilter(row, CUTOFF) iff LPF -> float64 (float32 on request),

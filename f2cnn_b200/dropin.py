@@ -28,6 +28,7 @@ _MODULES = {
     "scripts.processing.PHNFileReader": "f2cnn_b200.scripts.processing.PHNFileReader",
     "scripts.processing.LabelDataGenerator": "f2cnn_b200.scripts.processing.LabelDataGenerator",
     "scripts.CNN.Evaluating": "f2cnn_b200.scripts.CNN.Evaluating",
+    "scripts.plotting.PlottingProcessing": "f2cnn_b200.scripts.plotting.PlottingProcessing",
 }
 
 # names that reference modules bind with `from X import name`
@@ -50,6 +51,12 @@ _REBIND = {
         "EvaluateOneWavFile": ("scripts.CNN.Evaluating", "EvaluateOneWavFile"),
         "EvaluateRandom": ("scripts.CNN.Evaluating", "EvaluateRandom"),
         "EvaluateWithNoise": ("scripts.CNN.Evaluating", "EvaluateWithNoise"),
+        "PlotEnvelopesAndFormantsFromFile": ("scripts.plotting.PlottingProcessing", "PlotEnvelopesAndFormantsFromFile"),
+    },
+    # scripts/plotting/PlottingCNN.py:12
+    "scripts.plotting.PlottingCNN": {
+        "ReshapeEnvelopesForSpectrogram": ("scripts.plotting.PlottingProcessing", "ReshapeEnvelopesForSpectrogram"),
+        "PlotEnvelopeSpectrogram": ("scripts.plotting.PlottingProcessing", "PlotEnvelopeSpectrogram"),
     },
 }
 
@@ -61,7 +68,7 @@ def _ensure_parent_packages():
     (so that LabelDataGenerator, CNN, plotting ... keep resolving); otherwise this package's
     own `scripts` packages stand in, so that the hot-path modules import on their own."""
     for ref_pkg, ours in (("scripts", "f2cnn_b200.scripts"), ("scripts.processing", "f2cnn_b200.scripts.processing"),
-                          ("scripts.CNN", "f2cnn_b200.scripts.CNN")):
+                          ("scripts.CNN", "f2cnn_b200.scripts.CNN"), ("scripts.plotting", "f2cnn_b200.scripts.plotting")):
         if ref_pkg in sys.modules:
             continue
         try:
@@ -78,28 +85,31 @@ def _ensure_parent_packages():
 def install():
     """Idempotent.  Returns the dict {reference module path: drop-in module}."""
     _ensure_parent_packages()
+    displaced = {}
     for ref_name, ours in _MODULES.items():
         mod = importlib.import_module(ours)
         prev = sys.modules.get(ref_name)
         if prev is not None and prev is not mod:
             _installed.setdefault(ref_name, prev)
+            displaced[ref_name] = prev
         sys.modules[ref_name] = mod
         parent, _, leaf = ref_name.rpartition(".")
         if parent and parent in sys.modules:
             setattr(sys.modules[parent], leaf, mod)
     for importer, names in _REBIND.items():
-        m = sys.modules.get(importer)
-        if m is None:
-            continue
-        for attr, (src, name) in names.items():
-            if hasattr(m, attr):
-                setattr(m, attr, getattr(sys.modules[src], name))
+        # also the module object this call displaced: whoever imported it earlier still holds its functions
+        for m in (sys.modules.get(importer), displaced.get(importer)):
+            if m is None:
+                continue
+            for attr, (src, name) in names.items():
+                if hasattr(m, attr):
+                    setattr(m, attr, getattr(sys.modules[src], name))
     return {k: sys.modules[k] for k in _MODULES}
 
 
 def uninstall():
     """Restore whatever install() displaced (used by tests)."""
-    for ref_name in list(_MODULES) + ["scripts.CNN", "scripts.processing", "scripts"]:
+    for ref_name in list(_MODULES) + ["scripts.plotting", "scripts.CNN", "scripts.processing", "scripts"]:
         prev = _installed.pop(ref_name, None)
         if prev is not None:
             sys.modules[ref_name] = prev

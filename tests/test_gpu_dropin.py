@@ -247,3 +247,42 @@ def test_float32_npy_option_of_the_file_drivers(tree, oracle, monkeypatch):
         assert out.dtype == np.float32 and np.array_equal(out, np.concatenate(want))
     finally:
         dropin.uninstall()
+
+
+def test_plot_gtg_runs_on_the_decimated_envelope(tree, oracle, monkeypatch):
+    """`plot gtg` (scripts/plotting/PlottingProcessing.py:81-133): the image handed to imshow is the reference's
+    (every channel repeated by its ERB ratio) at every hop-th column, and the columns are the full-rate
+    envelope's own samples.  matplotlib is absent here: a recording stand-in takes the calls."""
+    import sys
+    import types
+    tmp_path, waves = tree
+    from f2cnn_b200 import api
+    from f2cnn_b200.gammatone import filters
+    from f2cnn_b200.scripts.plotting import PlottingProcessing as pp
+    w = waves[("TRAIN", "DR2.SPK1.SX7")]
+    co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, 100))
+    full = api.filterbank_envelope(w, co, False, 100)
+    for hop in (1, 7, 160):
+        g = api.gammatonegram(w, co, hop)
+        assert g.dtype == np.float64 and g.shape == (128, -(-len(w) // hop))
+        assert np.array_equal(g, full[:, ::hop])
+    assert rel(api.gammatonegram(w, co, 3), oracle.utterance(w, co, False, 100)[1][:, ::3]) <= TOL
+    calls = {}
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.imshow = lambda image, **kw: calls.update(image=image, kw=kw)
+    for name in ("plot", "legend", "text", "title", "show"):
+        setattr(plt, name, lambda *a, _n=name, **k: calls.setdefault(_n, []).append(a))
+    mpl = types.ModuleType("matplotlib")
+    colors = types.ModuleType("matplotlib.colors")
+    colors.LogNorm = lambda: "lognorm"
+    mpl.pyplot, mpl.colors = plt, colors
+    for name, mod in (("matplotlib", mpl), ("matplotlib.pyplot", plt), ("matplotlib.colors", colors)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    monkeypatch.setattr(pp, "MAX_COLUMNS", 1000)
+    path = str(tmp_path / "resources" / "f2cnn" / "TRAIN" / "DR2.SPK1.SX7.WAV")
+    pp.PlotEnvelopesAndFormantsFromFile(path, formantToPlot=2)
+    hop = -(-len(w) // 1000)
+    cfs = filters.centre_freqs(16000, 128, 100)
+    assert np.array_equal(calls["image"], pp.ReshapeEnvelopesForSpectrogram(full[:, ::hop], cfs))
+    assert calls["kw"]["extent"] == [0, calls["image"].shape[1] / (16000 / hop), 100, 8000]
+    assert len(calls["plot"]) == 1 and len(calls["show"]) == 1

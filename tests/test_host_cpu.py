@@ -137,7 +137,12 @@ def test_dropin_install_registers_reference_module_paths():
             assert callable(getattr(EnvelopeExtraction, name))
         for name in ("GetListOfEnvelopeFilesAndTimepoints", "GenerateInputData"):
             assert callable(getattr(InputGenerator, name))
-        assert len(mods) == 9
+        assert len(mods) == 10
+        from scripts.plotting import PlottingProcessing
+        assert PlottingProcessing.__name__.startswith("f2cnn_b200.")
+        for name in ("ERBScale", "GetNewHeightERB", "ReshapeEnvelopesForSpectrogram", "PlotEnvelopeSpectrogram",
+                     "PlotEnvelopesAndFormantsFromFile"):
+            assert callable(getattr(PlottingProcessing, name))
         from scripts.processing import FBFileReader, LabelDataGenerator, PHNFileReader
         for mod, names in ((LabelDataGenerator, ("ExtractLabel", "GenerateLabelData")),
                            (FBFileReader, ("ExtractFBFile", "GetFormantFrequencies", "GetFromantFrequenciesAround")),

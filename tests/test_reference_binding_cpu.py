@@ -80,7 +80,7 @@ def test_reference_cli_binds_to_the_dropin_and_signatures_match(clean_modules):
     # what the drop-in does not replace keeps coming from the reference tree
     assert f2cnn.OrganiseAllFiles.__module__ == "scripts.processing.OrganiseFiles"
     assert sys.modules["scripts.processing.OrganiseFiles"].__file__.startswith(REF)
-    assert f2cnn.PlotEnvelopesAndFormantsFromFile.__module__ == "scripts.plotting.PlottingProcessing"
+    assert f2cnn.PlotEnvelopesAndFormantsFromFile.__module__ == "f2cnn_b200.scripts.plotting.PlottingProcessing"
     # 3. every public function of the reference exists here with the same signature
     diffs = []
     for name in SHADOWED:
@@ -109,7 +109,7 @@ def test_late_install_rebinds_names_imported_by_value(clean_modules):
         fn = getattr(plotting, attr)
         assert fn.__module__.startswith("f2cnn_b200."), attr
     for attr in ("FilterAllOrganisedFiles", "ExtractAllEnvelopes", "GenerateInputData", "GenerateLabelData",
-                 "EvaluateOneWavFile", "EvaluateRandom", "EvaluateWithNoise"):
+                 "EvaluateOneWavFile", "EvaluateRandom", "EvaluateWithNoise", "PlotEnvelopesAndFormantsFromFile"):
         assert getattr(f2cnn, attr).__module__.startswith("f2cnn_b200."), attr
     # every name the reference module imports from a shadowed module is covered by the re-bind table
     import ast
@@ -117,3 +117,26 @@ def test_late_install_rebinds_names_imported_by_value(clean_modules):
     imported = {a.name for node in ast.walk(ast.parse(src)) if isinstance(node, ast.ImportFrom)
                 and node.module in dropin._MODULES for a in node.names}
     assert imported == set(dropin._REBIND["scripts.plotting.PlottingProcessing"])
+
+
+def test_gammatonegram_reshape_equals_the_reference(clean_modules):
+    """scripts/plotting/PlottingProcessing.py:18-60 (ERB row heights, row repetition, column slice) against the
+    drop-in's, and the signatures of its public functions (`axis` aside: the reference binds pyplot there)."""
+    import numpy as np
+    ref = importlib.import_module("scripts.plotting.PlottingProcessing")
+    assert ref.__file__.startswith(REF)
+    ours = importlib.import_module("f2cnn_b200.scripts.plotting.PlottingProcessing")
+    from f2cnn_b200.gammatone import filters
+    rng = np.random.default_rng(3)
+    for C, low in ((128, 100), (37, 50), (256, 20)):
+        cfs = filters.centre_freqs(16000, C, low)
+        env = rng.random((C, 300))
+        assert ours.GetNewHeightERB(env, cfs) == ref.GetNewHeightERB(env, cfs)
+        for start, end in ((0, None), (17, None), (5, 120)):
+            assert np.array_equal(ours.ReshapeEnvelopesForSpectrogram(env, cfs, start, end),
+                                  ref.ReshapeEnvelopesForSpectrogram(env, cfs, start, end))
+    for name, fn in _public_functions(ref).items():
+        theirs = [(p.name, p.default) for p in inspect.signature(fn).parameters.values() if p.name != "axis"]
+        mine = [(p.name, p.default) for p in inspect.signature(getattr(ours, name)).parameters.values()
+                if p.name not in ("axis", "NYQUIST")]
+        assert mine == theirs, name
