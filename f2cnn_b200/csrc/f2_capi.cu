@@ -619,9 +619,18 @@ static size_t ws_edge_bytes(const f2_batch* b) {
     return align_up((size_t)b->n_utts * (size_t)b->plan->C * 8 * sizeof(float), 256);
 }
 
+// Ring sections of the workspace: xz (two floats per ring sample) always; the two FFT scratch rings (the
+// second doubles as the per-utterance injection table) only when some utterance needs them -- a batch whose
+// rings are all transformed by the cluster kernel and read shared injection tables (every corpus batch)
+// holds (x, xi) alone: 8 bytes per ring sample instead of 16.
+static int ws_ring_units(const f2_batch* b) {
+    const bool compact = f2::ring_cluster_enabled() && b->private_g == 0 && b->min_log2 >= 15 && b->max_log2 <= 16;
+    return compact ? 2 : 4;
+}
+
 size_t f2_batch_workspace_bytes(const f2_batch* b, int want_full_gfb, int want_full_env) {
     if (!b) return 0;
-    size_t s = 4 * ws_ring_bytes(b->total_ring) + ws_edge_bytes(b);
+    size_t s = (size_t)ws_ring_units(b) * ws_ring_bytes(b->total_ring) + ws_edge_bytes(b);
     if (want_full_gfb) s += ws_full_bytes(b);
     if (want_full_env) s += ws_full_bytes(b);
     return s + 256;
@@ -668,11 +677,12 @@ int f2_batch_run(f2_batch* b, const f2_run_args* a, void* workspace, size_t work
 
     char* ws = (char*)align_up((size_t)workspace, 256);
     const size_t rb = ws_ring_bytes(b->total_ring);
-    float* Z = (float*)ws;
-    float2* xz = (float2*)(ws + rb);
-    float* G = (float*)(ws + 3 * rb);
-    float* edge = (float*)(ws + 4 * rb);
-    char* cur = ws + 4 * rb + ws_edge_bytes(b);
+    const int units = ws_ring_units(b);   // 2: no FFT scratch, no private injection tables (see ws_ring_units)
+    float* Z = units == 4 ? (float*)ws : nullptr;
+    float2* xz = (float2*)(units == 4 ? ws + rb : ws);
+    float* G = units == 4 ? (float*)(ws + 3 * rb) : nullptr;
+    float* edge = (float*)(ws + (size_t)units * rb);
+    char* cur = ws + (size_t)units * rb + ws_edge_bytes(b);
     float* gfb_t = nullptr;
     float* env_t = a->env_t;
     if (want_gfb) {

@@ -980,12 +980,16 @@ static int max_blocks(const HostPrepInfo& h, bool cols) {
     return best;
 }
 
+// development knob: F2CNN_B200_RING_CLUSTER=0 sends every size through the multi-pass kernels
+bool ring_cluster_enabled() {
+    static const bool on = [] { const char* v = getenv("F2CNN_B200_RING_CLUSTER"); return !(v && v[0] == '0'); }();
+    return on;
+}
+
 cudaError_t launch_prep(const PrepParams& p_in, const HostPrepInfo& h, cudaStream_t stream) {
     if (h.n_utts <= 0) return cudaSuccess;
-    // development knob: F2CNN_B200_RING_CLUSTER=0 sends every size through the multi-pass kernels
-    static const bool cluster_on = [] { const char* v = getenv("F2CNN_B200_RING_CLUSTER"); return !(v && v[0] == '0'); }();
     PrepParams p = p_in;
-    p.cluster = cluster_on && p.hilbert && h.min_log2N2 <= 16 && h.max_log2N2 >= 15;
+    p.cluster = ring_cluster_enabled() && p.hilbert && h.min_log2N2 <= 16 && h.max_log2N2 >= 15;
     if (h.max_log2N2 - 1 > 2 * kTwLog) return cudaErrorInvalidValue;
     // per device: the attribute belongs to the current device's copy of the function
     static bool attr_done[64] = {false};

@@ -33,6 +33,7 @@ constexpr int kGTabMinLog = 8, kGTabMaxLog = 20;   // ring sizes that share one 
 // device pointer to the four shifted copies (stride floats apart) of the table for N2 = 2^log2N2 on the
 // current device, or null (size out of range / out of memory: use per-utterance tables)
 const float* injection_table(int log2N2, int* stride);
+bool ring_cluster_enabled();   // false only under F2CNN_B200_RING_CLUSTER=0
 cudaError_t init_twiddles(cudaStream_t stream);
 cudaError_t launch_prep(const PrepParams& p, const HostPrepInfo& h, cudaStream_t stream);
 
