@@ -215,9 +215,9 @@ struct OutCtx {
     float env_scale;  // g4 (no low-pass) or g4*b0 (low-pass): applied when a value is stored
     int wk;         // OUT 3: index (within the utterance) of the next decimated frame
     int nwin;       // OUT 3: windows of this utterance
-    // CN: (C, n) outputs in the reference's layout.  Each lane stages its channel's samples in a 32 x 33
-    // shared-memory tile; every 32 samples the warp writes the tile out row by row -- 32 consecutive samples
-    // of one channel per store instruction (128 / 256 contiguous bytes) instead of a time-major scratch
+    // CN: (C, n) outputs in the reference's layout.  Each lane stages its channel's samples in a 32 x (kCnW+1)
+    // shared-memory tile; every kCnW samples the warp writes the tile out row by row -- 32 consecutive samples
+    // of one channel per store instruction (128 / 256 contiguous bytes), kCnW per row instead of a time-major scratch
     // matrix and a transposing second kernel.
     float* tr_g;    // shared-memory tiles (or null)
     float* tr_e;
@@ -228,6 +228,14 @@ struct OutCtx {
     int cn_f64;
 };
 
+// (C, n) staging tile: 32 channels x kCnW samples (+1 column of padding).  Longer runs per channel row make
+// the stores friendlier to DRAM pages (every row of a tile lands in a different page of the (C, n) matrix).
+#ifndef F2_CN_W
+#define F2_CN_W 128
+#endif
+constexpr int kCnW = F2_CN_W;
+constexpr int kCnP = kCnW + 1;
+
 // rows of the staged tile -> global: samples [tb, tb + cnt) of every channel of this CTA
 __device__ __forceinline__ void flush_cn(const float* tr, char* base, const OutCtx& o, int tb, int cnt) {
     __syncwarp();
@@ -235,11 +243,15 @@ __device__ __forceinline__ void flush_cn(const float* tr, char* base, const OutC
     if (o.cn_f64) {
         double* row = reinterpret_cast<double*>(base) + tb + lane;
         for (int r = 0; r < o.cn_rows; ++r, row += o.cn_n)
-            if (lane < cnt) __stcs(row, (double)tr[r * 33 + lane]);
+#pragma unroll
+            for (int h = 0; h < kCnW; h += 32)
+                if (lane + h < cnt) __stcs(row + h, (double)tr[r * kCnP + lane + h]);
     } else {
         float* row = reinterpret_cast<float*>(base) + tb + lane;
         for (int r = 0; r < o.cn_rows; ++r, row += o.cn_n)
-            if (lane < cnt) __stcs(row, tr[r * 33 + lane]);
+#pragma unroll
+            for (int h = 0; h < kCnW; h += 32)
+                if (lane + h < cnt) __stcs(row + h, tr[r * kCnP + lane + h]);
     }
     __syncwarp();
 }
@@ -317,11 +329,11 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
                 }
             }
             if (OUT == 2 && CN) {
-                const int col = (t + i + j) & 31;
-                if (o.cn_g) o.tr_g[threadIdx.x * 33 + col] = k.g4 * y.x;
+                const int col = (t + i + j) & (kCnW - 1);
+                if (o.cn_g) o.tr_g[threadIdx.x * kCnP + col] = k.g4 * y.x;
                 if (ENV > 0 && o.cn_e) {
                     const float v = ENV == 2 ? ev[j] + (j > 0 ? ev[j > 0 ? j - 1 : 0] : wprev) : ev[j];
-                    o.tr_e[threadIdx.x * 33 + col] = o.env_scale * v;
+                    o.tr_e[threadIdx.x * kCnP + col] = o.env_scale * v;
                 }
             }
         }
@@ -330,9 +342,9 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             if (o.gfb) o.gfb += U * o.C;
             if (o.env) o.env += U * o.C;
         }
-        if (OUT == 2 && CN && ((t + i + U) & 31) == 0) {
-            if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + i + U - 32, 32);
-            if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + i + U - 32, 32);
+        if (OUT == 2 && CN && ((t + i + U) & (kCnW - 1)) == 0) {
+            if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + i + U - kCnW, kCnW);
+            if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + i + U - kCnW, kCnW);
         }
         if (OUT > 0 && ENV > 0 && o.dec) {
             while (o.next_dec < t + i + U) {
@@ -374,12 +386,12 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             }
         }
         if (OUT == 2 && CN) {
-            const int col = (t + i) & 31;
-            if (o.cn_g) o.tr_g[threadIdx.x * 33 + col] = k.g4 * y.x;
-            if (ENV > 0 && o.cn_e) o.tr_e[threadIdx.x * 33 + col] = o.env_scale * out;
-            if (col == 31) {
-                if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + i - 31, 32);
-                if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + i - 31, 32);
+            const int col = (t + i) & (kCnW - 1);
+            if (o.cn_g) o.tr_g[threadIdx.x * kCnP + col] = k.g4 * y.x;
+            if (ENV > 0 && o.cn_e) o.tr_e[threadIdx.x * kCnP + col] = o.env_scale * out;
+            if (col == kCnW - 1) {
+                if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + i - (kCnW - 1), kCnW);
+                if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + i - (kCnW - 1), kCnW);
             }
         }
         if (OUT > 0 && ENV > 0 && o.dec && o.next_dec == t + i) {
@@ -392,8 +404,8 @@ __device__ __forceinline__ void run_tile(const FusedParams& p, const Coef& k, St
             o.next_dec += o.step;
         }
     }
-    if (OUT == 2 && CN && ((t + cnt) & 31) != 0) {   // the utterance ends inside a block of 32
-        const int rest = (t + cnt) & 31;
+    if (OUT == 2 && CN && ((t + cnt) & (kCnW - 1)) != 0) {   // the utterance ends inside a block of kCnW
+        const int rest = (t + cnt) & (kCnW - 1);
         if (o.cn_g) flush_cn(o.tr_g, o.cn_g, o, t + cnt - rest, rest);
         if (ENV > 0 && o.cn_e) flush_cn(o.tr_e, o.cn_e, o, t + cnt - rest, rest);
     }
@@ -403,7 +415,7 @@ struct Smem {
     float2 (*xz)[kTile];
     float (*g)[kTile];
     uint64_t* full;
-    float* tr;   // CN: two 32 x 33 transposition tiles
+    float* tr;   // CN: two 32 x (kCnW + 1) transposition tiles
 };
 
 // The whole CTA (= one warp = 32 adjacent channels) for one section form.
@@ -511,7 +523,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p, const Item& ite
         const size_t esize = p.cn_f64 ? 8 : 4;
         const size_t block = ((size_t)ut.full_off * o.C + (size_t)c0 * (size_t)n) * esize;   // (C, n_u) blocks back to back
         o.tr_g = sm.tr;
-        o.tr_e = sm.tr + 32 * 33;
+        o.tr_e = p.gfb_cn ? sm.tr + 32 * kCnP : sm.tr;   // envelope alone: the only tile
         o.cn_g = p.gfb_cn ? reinterpret_cast<char*>(p.gfb_cn) + block : nullptr;
         o.cn_e = p.env_cn ? reinterpret_cast<char*>(p.env_cn) + block : nullptr;
     }
@@ -606,7 +618,7 @@ __global__ void __launch_bounds__(kChanPerBlock, MINB) fused_kernel(const FusedP
     __shared__ __align__(128) float2 s_xz[kStages][kTile];
     __shared__ __align__(128) float s_g[kStages][kTile];
     __shared__ __align__(8) uint64_t s_full[kStages];
-    __shared__ float s_tr[CN ? 2 * 32 * 33 : 1];
+    extern __shared__ float s_tr[];   // CN: one 32 x (kCnW + 1) staging tile per (C, n) output (dynamic: 0, 1 or 2 tiles)
     if (threadIdx.x == 0) {
         for (int b = 0; b < kStages; ++b) mbar_init(&s_full[b], 1);
         mbar_fence_init();
@@ -633,8 +645,9 @@ static void launch_variant(const FusedParams& p, int n_items, cudaStream_t strea
         else fused_kernel<MINB, U, false, true, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
     } else if (p.gfb_cn || p.env_cn) {
         // (C, n) outputs written by the kernel itself (own instantiation: two transposition tiles per CTA)
-        if (p.edge) fused_kernel<MINB, U, true, false, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
-        else fused_kernel<MINB, U, false, false, true><<<n_items, kChanPerBlock, 0, stream>>>(p);
+        const size_t tiles = ((p.gfb_cn ? 1 : 0) + (p.env_cn ? 1 : 0)) * (size_t)(32 * kCnP) * sizeof(float);
+        if (p.edge) fused_kernel<MINB, U, true, false, true><<<n_items, kChanPerBlock, tiles, stream>>>(p);
+        else fused_kernel<MINB, U, false, false, true><<<n_items, kChanPerBlock, tiles, stream>>>(p);
     } else {
         if (p.edge) fused_kernel<MINB, U, true, false, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
         else fused_kernel<MINB, U, false, false, false><<<n_items, kChanPerBlock, 0, stream>>>(p);
