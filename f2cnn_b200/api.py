@@ -469,6 +469,109 @@ def features_to_windows(waves, coefs, timepoints, LPF=False, CUTOFF=100, radius=
     return host
 
 
+class FrameWindows:
+    """The input tensor of a corpus WITHOUT its (2R+1)-fold redundancy: the decimated envelope frames of every
+    utterance in one page-locked host array, and the windows as overlapping VIEWS of it.
+
+    Row k of utterance u of `input_data.npy` is frames k .. k+dots-1 of that utterance
+    (InputGenerator.py:73-80 on the label grid of LabelDataGenerator.py:38-50), i.e. dots*C consecutive floats
+    starting at frame frame_offsets[u] + k: `windows(u)` is that (counts[u], dots, C) array as a strided view,
+    `self[r]` is global row r, `materialize()` builds the reference's tensor (bit-identical to
+    api.features_to_windows).  0.71 GB instead of 7.5 GB for the 4620-utterance corpus: a consumer that reads
+    windows through the views (a training loop that gathers mini-batches) never pays for the expansion, which is
+    what bounds the end-to-end time of the full tensor on any number of GPUs.
+
+    `frames` belongs to the cached pipeline of this corpus layout: it is valid until the next
+    features_to_frames / features_to_windows call with the same lengths (copy it to keep it)."""
+
+    def __init__(self, frames, frame_offsets, counts, dots, utterances, placer):
+        self.frames, self.frame_offsets, self.counts, self.dots = frames, frame_offsets, counts, int(dots)
+        self.utterances = utterances          # indices into the caller's utterance list (a shard holds a subset)
+        self.row_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self._placer = placer
+
+    def __len__(self):
+        return int(self.row_offsets[-1])
+
+    def windows(self, u):
+        """(counts[u], dots, C) float32 view of the u-th utterance held here (no copy)."""
+        C = self.frames.shape[1]
+        k, f0 = int(self.counts[u]), int(self.frame_offsets[u])
+        if k == 0:
+            return np.zeros((0, self.dots, C), dtype=np.float32)
+        base = self.frames[f0:f0 + k + self.dots - 1]
+        return np.lib.stride_tricks.as_strided(base, shape=(k, self.dots, C), strides=(C * 4, C * 4, 4), writeable=False)
+
+    def __getitem__(self, r):
+        r = int(r)
+        if r < 0:
+            r += len(self)
+        if not 0 <= r < len(self):
+            raise IndexError("row %d of %d" % (r, len(self)))
+        u = int(np.searchsorted(self.row_offsets, r, side="right") - 1)
+        f = int(self.frame_offsets[u]) + r - int(self.row_offsets[u])
+        return self.frames[f:f + self.dots]
+
+    def materialize(self, out=None):
+        """The (N, dots, C) float32 tensor of the reference, rows placed by the library's host pool."""
+        C = self.frames.shape[1]
+        out = engine.host_empty((len(self), self.dots, C), np.float32) if out is None else out
+        runs = np.stack([self.frame_offsets[:-1], self.row_offsets[:-1], self.counts], axis=1).astype(np.int64)
+        runs = np.ascontiguousarray(runs[runs[:, 2] > 0])
+        if runs.shape[0]:
+            self._placer.submit(torch.from_numpy(self.frames), runs, out, dots=self.dots, stream=None, after_stream=False)
+            self._placer.wait()
+        return out
+
+
+def features_to_frames(waves, coefs, LPF=False, CUTOFF=100, radius=5, step=160, counts=None, shard=None):
+    """Waveforms -> FrameWindows: the same filterbank -> envelope -> decimation as features_to_windows on the
+    label grid (window k of an utterance is centred on step*radius + step*k, LabelDataGenerator.py:38-50), but the
+    call ends when the decimated frames are on the host -- nothing is expanded.  waves: (flat, lengths) or a list
+    of 1-D arrays; counts[u]: windows of utterance u (default: the label grid's int(n/step - dots - 1));
+    shard=(rank, world): this process computes the utterances engine.shard_utterances deals to `rank`
+    (FrameWindows.utterances)."""
+    coefs = np.asarray(coefs, dtype=np.float64)
+    plan = engine.plan_for(coefs)
+    dots = 2 * radius + 1
+    flat_in = None
+    if isinstance(waves, tuple) and len(waves) == 2:
+        flat_in, lengths = waves
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        if not torch.is_tensor(flat_in):
+            flat_in = torch.from_numpy(_as_wave(flat_in))
+        if flat_in.dim() != 1 or flat_in.numel() != int(lengths.sum()):
+            raise ValueError("flat buffer holds %d samples, lengths add up to %d" % (flat_in.numel(), int(lengths.sum())))
+    else:
+        waves = [_as_wave(w) for w in waves]
+        if len({w.dtype for w in waves}) > 1:
+            waves = [w.astype(np.float64) for w in waves]
+        lengths = np.asarray([w.shape[0] for w in waves], dtype=np.int64)
+    n_frames = (lengths + step - 1) // step
+    grid = np.maximum((lengths / step - dots - 1).astype(np.int64), 0)
+    if counts is None:
+        counts = grid
+    else:
+        counts = np.ascontiguousarray(counts, dtype=np.int64).reshape(-1)
+        if counts.shape[0] != lengths.shape[0] or np.any(counts < 0) or np.any(counts + dots - 1 > np.maximum(n_frames, dots - 1)):
+            raise IndexError("counts: one entry per utterance, windows must lie inside the utterance's frames")
+    sel, src_offsets, share = np.arange(lengths.shape[0]), None, 1
+    if shard is not None:
+        rank, world = int(shard[0]), int(shard[1])
+        if not 0 <= rank < world:
+            raise ValueError("shard=(rank, world) needs 0 <= rank < world")
+        sel = engine.shard_utterances(lengths, world)[rank]
+        src_offsets = (np.cumsum(lengths) - lengths)[sel]
+        share = world
+    pipe = _pipeline_for(plan, lengths[sel], dots, step, 0, LPF, CUTOFF, src_offsets, share)
+    no_runs = np.zeros((0, 3), dtype=np.int64)
+    if flat_in is not None:
+        pipe.run(flat_in, no_runs, None)
+    else:
+        pipe.run([waves[u] for u in sel], no_runs, None)
+    return FrameWindows(pipe._dec_host.numpy(), pipe.frame_offsets, counts[sel], dots, sel, pipe.placer)
+
+
 def dense_frames(wave, coefs, LPF=False, CUTOFF=100, radius=5, step=160, normalize=True, dtype=np.float64,
                  frames=None):
     """In-memory front end of Evaluating.EvaluateOneWavArray (Evaluating.py:52-80):

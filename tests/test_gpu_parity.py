@@ -664,3 +664,44 @@ def test_pinned_block_is_addressable_from_kernels(gpu):
     batch.run(torch.from_numpy(w).cuda(), lpf=True, cutoff=50, out={"dec": host})
     torch.cuda.synchronize()
     assert np.array_equal(host.numpy(), dev.cpu().numpy())
+
+
+def test_frame_windows_are_views_of_the_decimated_frames(gpu, monkeypatch):
+    """api.features_to_frames: the windows of the label grid as overlapping views of the decimated frames --
+    equal, bit for bit, to the rows api.features_to_windows builds on its corpus path (whole utterances);
+    materialize() is that tensor; a shard holds its own utterances only."""
+    api, engine, filters, torch = gpu
+    monkeypatch.setattr(api, "_PIPELINE_BYTES", 0)   # a small corpus takes the corpus path too
+    from f2cnn_b200 import synth
+    co = coefs128()
+    rng = np.random.default_rng(17)
+    lens = rng.integers(1500, 9000, size=37).astype(np.int64)
+    lens[5] = 1700                       # too short for a single window of the grid: 0 rows
+    waves = [synth.white_noise_i16(int(n), seed=300 + i) for i, n in enumerate(lens)]
+    nwin = np.maximum((lens / 160 - 12).astype(np.int64), 0)
+    assert nwin[5] == 0
+    centers = [800 + 160 * np.arange(k, dtype=np.int64) for k in nwin]
+    want = api.features_to_windows(waves, co, centers, True, 50)
+    flat = torch.from_numpy(np.concatenate(waves))
+    for source in (waves, (flat, lens)):
+        fw = api.features_to_frames(source, co, True, 50)
+        assert len(fw) == want.shape[0] and np.array_equal(fw.counts, nwin)
+        row = 0
+        for u, k in enumerate(nwin):
+            v = fw.windows(u)
+            assert v.shape == (k, 11, 128) and (k == 0 or not v.flags["OWNDATA"])
+            assert np.array_equal(v, want[row:row + k]), u
+            row += int(k)
+        for r in (0, 1, int(nwin[0]), want.shape[0] - 1, -1):
+            assert np.array_equal(fw[r], want[r])
+        with pytest.raises(IndexError):
+            fw[want.shape[0]]
+        assert np.array_equal(fw.materialize(), want)
+    halves = [api.features_to_frames((flat, lens), co, True, 50, shard=(r, 2)) for r in range(2)]
+    assert sorted(np.concatenate([h.utterances for h in halves]).tolist()) == list(range(37))
+    first_row = np.concatenate([[0], np.cumsum(nwin)])
+    for h in halves[::-1]:               # the second shard's buffer is still its own (another pipeline)
+        for j, u in enumerate(h.utterances):
+            assert np.array_equal(h.windows(j), want[first_row[u]:first_row[u + 1]]), u
+    with pytest.raises(IndexError):
+        api.features_to_frames(waves, co, True, 50, counts=nwin + 3)
