@@ -525,6 +525,19 @@ class WindowPipeline:
         numpy arrays; runs: (n, 3) int64 from engine.window_runs on this pipeline's frame_offsets;
         out_host: the (N, dots, C) float32 host array or tensor the rows go to (any host memory).
         Returns when every row has been placed."""
+        # no garbage-collector pause while the launch sequence is being queued: a generation-0/1 sweep of a
+        # torch process takes ~5 ms, and when it hit between the kernel launches and the placement submits one
+        # call in six finished 4 ms late (tools/e2e_hiccup.py); collection resumes while this thread waits
+        import gc
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            return self._run(wave_host, runs, out_host, keep_frames, gc_was_on)
+        finally:
+            if gc_was_on:
+                gc.enable()
+
+    def _run(self, wave_host, runs, out_host, keep_frames, gc_was_on):
         caller = torch.cuda.current_stream(self.plan.device)
         dev = self.plan.device
         C = self.plan.n_channels
@@ -600,6 +613,9 @@ class WindowPipeline:
             self._ev_end.record(self._s_out)
         for s_ in (self._s_out, self._s_comp[0], self._s_comp[1]):
             caller.wait_stream(s_)
+        if gc_was_on:
+            import gc
+            gc.enable()                 # everything is queued: a sweep now costs nothing
         self._ev_end.synchronize()      # blocking event: the waiting thread sleeps, its core places rows
         self._s_out.synchronize()
         self.placer.wait()
