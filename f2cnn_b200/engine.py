@@ -444,6 +444,12 @@ class WindowPipeline:
         n_sub = max(1, min(int(n_sub), 32, max(U, 1)))
         per_sub = cum[-1] / n_sub
         head, size, at = [], per_sub / 8, 0.0
+        ramp = os.environ.get("F2CNN_B200_RAMP")   # development knob: head sub-batches as fractions 1/d of the corpus
+        if ramp:
+            for d in ramp.split(","):
+                at += cum[-1] / float(d)
+                head.append(at)
+            size = per_sub
         while size < per_sub and at + size < cum[-1] / 2:
             at += size
             head.append(at)
