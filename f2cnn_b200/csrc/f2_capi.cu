@@ -624,7 +624,7 @@ static size_t ws_edge_bytes(const f2_batch* b) {
 // rings are all transformed by the cluster kernel and read shared injection tables (every corpus batch)
 // holds (x, xi) alone: 8 bytes per ring sample instead of 16.
 static int ws_ring_units(const f2_batch* b) {
-    const bool compact = f2::ring_cluster_enabled() && b->private_g == 0 && b->min_log2 >= 15 && b->max_log2 <= 16;
+    const bool compact = f2::ring_cluster_enabled() && b->private_g == 0 && b->min_log2 >= 15 && b->max_log2 <= 17;
     return compact ? 2 : 4;
 }
 

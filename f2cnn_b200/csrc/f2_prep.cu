@@ -46,6 +46,7 @@ __global__ void init_twiddle_kernel() {
 // g_step15[k1*256 + n2] = exp(-2*pi*i*n2*k1/2^15), k1 < 128 (384 KB, L2-resident; the inverse conjugates)
 __device__ float2 g_step14[1 << 14];
 __device__ float2 g_step15[1 << 15];
+__device__ float2 g_step16[1 << 16];   // [k1*256 + n2] = exp(-2*pi*i*n2*k1/2^16), k1 < 256
 
 __global__ void init_step_twiddle_kernel() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,11 +59,15 @@ __global__ void init_step_twiddle_kernel() {
         sincospi(-2.0 * (double)((i & 255) * (i >> 8)) / (double)(1 << 15), &s, &c);
         g_step15[i] = make_float2((float)c, (float)s);
     }
+    if (i < (1 << 16)) {
+        sincospi(-2.0 * (double)((i & 255) * (i >> 8)) / (double)(1 << 16), &s, &c);
+        g_step16[i] = make_float2((float)c, (float)s);
+    }
 }
 
 cudaError_t init_twiddles(cudaStream_t stream) {
     init_twiddle_kernel<<<(1 << (kTwLog - 1)) / 256, 256, 0, stream>>>();
-    init_step_twiddle_kernel<<<(1 << 15) / 256, 256, 0, stream>>>();
+    init_step_twiddle_kernel<<<(1 << 16) / 256, 256, 0, stream>>>();
     return cudaGetLastError();
 }
 
@@ -171,8 +176,8 @@ __device__ __forceinline__ void smem_fft(float2* s, int pitch, int logL, int bat
     }
 }
 
-// N2 = 32768 / 65536 are transformed by one cluster kernel (ring_cluster_kernel below)
-__host__ __device__ inline bool ring_cluster_size(int log2N2) { return log2N2 == 15 || log2N2 == 16; }
+// N2 = 32768 / 65536 / 131072 are transformed by one cluster kernel (ring_cluster_kernel, ring_cluster8_kernel below)
+__host__ __device__ inline bool ring_cluster_size(int log2N2) { return log2N2 >= 15 && log2N2 <= 17; }
 
 // legs of 128 / 256 points have a register-pass implementation (see the fast kernels below)
 __host__ __device__ inline bool fast_leg(int l) { return l == 7 || l == 8; }
@@ -350,6 +355,10 @@ __device__ __forceinline__ void fft8(float2 (&v)[8]) {
     }
 }
 __device__ __forceinline__ constexpr int out8(int r) { return (r >> 1) + 4 * (r & 1); }
+// 8- or 16-point register transform chosen by the array length
+template <bool INV> __device__ __forceinline__ void fft_rc(float2 (&v)[8]) { fft8<INV>(v); }
+template <bool INV> __device__ __forceinline__ void fft_rc(float2 (&v)[16]) { fft16<INV>(v); }
+template <int R> __device__ __forceinline__ constexpr int out_rc(int r) { return R == 16 ? out16(r) : out8(r); }
 
 template <bool INV>
 __device__ __forceinline__ float2 leg_twiddle(int m, int logL) {  // w_L^m for 0 <= m < L
@@ -594,12 +603,12 @@ __global__ void plain_ring_kernel(PrepParams p, int only_tiny) {
 
 
 // =============================================================================================
-// The whole ring transform of an utterance in ONE kernel (N2 = 32768 and 65536, the sizes corpus
-// utterances have): a thread-block cluster keeps the packed spectrum in its distributed shared
+// The whole ring transform of an utterance in ONE kernel (N2 = 32768, 65536 and 131072: utterances of
+// 1 ... 8.2 s): a thread-block cluster keeps the packed spectrum in its distributed shared
 // memory, so HBM sees the wave once (plus one L2-resident re-read) and the (x, xi) ring once --
 // 0.6 MB per utterance where the five-kernel sequence above moves 3 MB through two scratch rings.
 //
-//   M = N2/2 = 128 x M2 packed complex points z[n1*M2 + n2].  CTA `rank` of the CL in the cluster owns
+//   M = N2/2 = M1 x M2 packed complex points z[n1*M2 + n2] (M1 = 128; 256 for N2 = 131072, in a cluster of 8).  CTA `rank` of the CL in the cluster owns
 //   columns [rank*M2/CL, +M2/CL) in the column phases and a mirror-closed set of 128/CL rows in the row
 //   phase (row k1 and row 128-k1 sit in adjacent slots, because the Hilbert step pairs Z[k] with Z[M-k]).
 //   1  columns forward: 128-point FFTs (16 x 8 in registers around one shared exchange), read straight
@@ -613,9 +622,10 @@ __global__ void plain_ring_kernel(PrepParams p, int only_tiny) {
 //      (x[2m], x[2m+1]) as one float4 of the interleaved ring, 512 contiguous bytes per warp.
 // =============================================================================================
 
-template <int L2, int CL, int T>
+template <int L1, int L2, int CL, int T>
 struct RingCl {
-    static constexpr int M1 = 128, M2 = 1 << L2, M = M1 * M2;
+    static constexpr int M1 = 1 << L1, M2 = 1 << L2, M = M1 * M2;
+    static constexpr int RC = M1 / 16;   // second radix of the column transform: 8 (128 points) or 16 (256)
     static constexpr int NC = M2 / CL;   // columns per CTA
     static constexpr int NR = M1 / CL;   // rows per CTA
     static constexpr int PC = M1 + 1;    // column pitch (float2): odd, so that column-major tasks spread over the banks
@@ -625,8 +635,8 @@ struct RingCl {
     static constexpr int kE1 = (NC * PC > NR * PR) ? NC * PC : NR * PR;
     static constexpr int kElems = kE1 > M1 * PB3 ? kE1 : M1 * PB3;
     __device__ static __forceinline__ int pad(int q) { return q + (q >> PSH); }
-    // row k1 -> (owner CTA, slot).  f = min(k1, 128-k1); rows f and 128-f go to CTA f % CL, slots 2*(f/CL)
-    // and 2*(f/CL)+1; the two self-mirrored rows 0 and 64 share pair 0 of CTA 0.
+    // row k1 -> (owner CTA, slot).  f = min(k1, M1-k1); rows f and M1-f go to CTA f % CL, slots 2*(f/CL)
+    // and 2*(f/CL)+1; the two self-mirrored rows 0 and M1/2 share pair 0 of CTA 0.
     __device__ static __forceinline__ void owner(int k1, int& cta, int& slot) {
         const int f = k1 <= M1 / 2 ? k1 : M1 - k1;
         cta = f % CL;
@@ -642,15 +652,16 @@ struct RingCl {
     __device__ static __forceinline__ int pos(int k2) { return pad((k2 & 15) * (M2 / 16) + (k2 >> 4)); }
 };
 
-template <int L2, int CL, int T>
+template <int L1, int L2, int CL, int T>
 __device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const UttDesc& ut, float2* sm) {
-    using S = RingCl<L2, CL, T>;
+    using S = RingCl<L1, L2, CL, T>;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x;
     constexpr int M2 = S::M2, NC = S::NC, NR = S::NR, PC = S::PC, PR = S::PR;
     constexpr int R2 = M2 / 16;           // second radix of the row transform (16 or 8)
+    constexpr int RC = S::RC;             // ... of the column transform
     const float invN = 0.5f / (float)S::M;
     // leg twiddles in shared memory behind the data, the index that varies across the threads of a warp
     // innermost: tw_a[k*8 + n] = w_128^(k*n) (k < 16, n < 8), tw_b[k*16 + n] = w_128^(k*n) (k < 8, n < 16),
@@ -662,41 +673,42 @@ __device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const Utt
         tw_a[i] = leg_twiddle<false>((i >> 3) * (i & 7), 7);
         tw_b[i] = leg_twiddle<false>((i >> 4) * (i & 15), 7);
     }
-    if (L2 == 8)
+    if (L2 == 8 || L1 == 8)
         for (int i = tid; i < 256; i += T) tw_r[i] = leg_twiddle<false>((i >> 4) * (i & 15), 8);
-    const float2* __restrict__ step = L2 == 7 ? g_step14 : g_step15;   // [k1*M2 + n2]
+    const float2* __restrict__ step = L1 + L2 == 14 ? g_step14 : (L1 + L2 == 15 ? g_step15 : g_step16);   // [k1*M2 + n2]
+    const float2* tw_c = L1 == 8 ? tw_r : tw_a;   // column legs: [k*RC + n] = w_M1^(k*n)
     __syncthreads();
 
     // ---- 1: columns forward ----
-    for (int task = tid; task < NC * 8; task += T) {
+    for (int task = tid; task < NC * RC; task += T) {
         const int b = task % NC, n2p = task / NC;
         float2 v[16];
 #pragma unroll
         for (int n1p = 0; n1p < 16; ++n1p)
-            v[n1p] = load_pair(p.wave, p.wave_dtype, ut.wave_off, (n1p * 8 + n2p) * M2 + rank * NC + b, ut.n);
+            v[n1p] = load_pair(p.wave, p.wave_dtype, ut.wave_off, (n1p * RC + n2p) * M2 + rank * NC + b, ut.n);
         fft16<false>(v);
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int k1p = out16(r);
-            sm[b * PC + k1p * 8 + n2p] = cmul(v[r], tw_a[k1p * 8 + n2p]);
+            sm[b * PC + k1p * RC + n2p] = cmul(v[r], tw_c[k1p * RC + n2p]);
         }
     }
     __syncthreads();
     {
         constexpr int NT = NC * 16 / T;
         static_assert(NT * T == NC * 16, "column pass 2 tasks must divide evenly");
-        float2 h[NT][8];
+        float2 h[NT][RC];
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
             const int task = tid + i * T;
             const int b = task % NC, k1p = task / NC;
 #pragma unroll
-            for (int n2p = 0; n2p < 8; ++n2p) h[i][n2p] = sm[b * PC + k1p * 8 + n2p];
-            fft8<false>(h[i]);
+            for (int n2p = 0; n2p < RC; ++n2p) h[i][n2p] = sm[b * PC + k1p * RC + n2p];
+            fft_rc<false>(h[i]);
             const int n2 = rank * NC + b;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int k1 = k1p + 16 * out8(r);
+            for (int r = 0; r < RC; ++r) {
+                const int k1 = k1p + 16 * out_rc<RC>(r);
                 h[i][r] = cmul(h[i][r], __ldg(step + k1 * M2 + n2));
             }
         }
@@ -707,9 +719,9 @@ __device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const Utt
             const int b = task % NC, k1p = task / NC;
             const int n2 = rank * NC + b;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < RC; ++r) {
                 int cta, slot;
-                S::owner(k1p + 16 * out8(r), cta, slot);
+                S::owner(k1p + 16 * out_rc<RC>(r), cta, slot);
                 float2* dst = cluster.map_shared_rank(sm, cta);
                 dst[slot * PR + S::pad(n2)] = h[i][r];
             }
@@ -862,17 +874,17 @@ __device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const Utt
     }
 
     // ---- 3: columns inverse (data as [k1][b]), ring store ----
-    for (int task = tid; task < NC * 8; task += T) {
+    for (int task = tid; task < NC * RC; task += T) {
         const int b = task % NC, n2p = task / NC;
         float2* col = sm + b;
         float2 v[16];
 #pragma unroll
-        for (int n1p = 0; n1p < 16; ++n1p) v[n1p] = col[(n1p * 8 + n2p) * S::PB3];
+        for (int n1p = 0; n1p < 16; ++n1p) v[n1p] = col[(n1p * RC + n2p) * S::PB3];
         fft16<true>(v);
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int k1p = out16(r);
-            col[(k1p * 8 + n2p) * S::PB3] = cmul(v[r], cconj(tw_a[k1p * 8 + n2p]));
+            col[(k1p * RC + n2p) * S::PB3] = cmul(v[r], cconj(tw_c[k1p * RC + n2p]));
         }
     }
     __syncthreads();
@@ -880,16 +892,22 @@ __device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const Utt
     for (int task = tid; task < NC * 16; task += T) {
         const int b = task % NC, k1p = task / NC;
         const float2* col = sm + b;
-        float2 v[8], x[8];
+        float2 v[RC], x[8];
+        if (RC == 8) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r)   // the wave again (L2): issued before the transform that hides their latency
-            x[r] = load_pair(p.wave, p.wave_dtype, ut.wave_off, (k1p + 16 * out8(r)) * M2 + rank * NC + b, ut.n);
+            for (int r = 0; r < 8; ++r)   // the wave again (L2): issued before the transform that hides their latency
+                x[r] = load_pair(p.wave, p.wave_dtype, ut.wave_off, (k1p + 16 * out8(r)) * M2 + rank * NC + b, ut.n);
+        }
 #pragma unroll
-        for (int n2p = 0; n2p < 8; ++n2p) v[n2p] = col[(k1p * 8 + n2p) * S::PB3];
-        fft8<true>(v);
+        for (int n2p = 0; n2p < RC; ++n2p) v[n2p] = col[(k1p * RC + n2p) * S::PB3];
+        fft_rc<true>(v);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            ring[(k1p + 16 * out8(r)) * M2 + rank * NC + b] = make_float4(x[r].x, v[r].x, x[r].y, v[r].y);
+        for (int r = 0; r < RC; ++r) {
+            const int m = (k1p + 16 * out_rc<RC>(r)) * M2 + rank * NC + b;
+            // 16 results per thread: no registers left to hold the wave pairs across the transform
+            const float2 xv = RC == 8 ? x[r & 7] : load_pair(p.wave, p.wave_dtype, ut.wave_off, m, ut.n);
+            ring[m] = make_float4(xv.x, v[r].x, xv.y, v[r].y);
+        }
     }
 }
 
@@ -902,31 +920,46 @@ __device__ __forceinline__ void ring_cluster_body(const PrepParams& p, const Utt
 constexpr int kRingCl = F2_RING_CL;   // CTAs per cluster
 constexpr int kRingClThreads = 512;
 constexpr int kRingAhead = 148 * F2_RING_CTAS / F2_RING_CL;   // clusters resident at a time
-constexpr int kRingClSmem =
-    (RingCl<8, kRingCl, kRingClThreads>::kElems > RingCl<7, kRingCl, kRingClThreads>::kElems
-         ? RingCl<8, kRingCl, kRingClThreads>::kElems
-         : RingCl<7, kRingCl, kRingClThreads>::kElems) * (int)sizeof(float2) + 512 * (int)sizeof(float2);
+constexpr int kRingCl8 = 8;           // CTAs per cluster for rings of 131072 samples (M = 256 x 256)
+constexpr int kRingAhead8 = 148 * F2_RING_CTAS / kRingCl8;
+constexpr int kRingClElems = RingCl<7, 8, kRingCl, kRingClThreads>::kElems > RingCl<7, 7, kRingCl, kRingClThreads>::kElems
+                                 ? RingCl<7, 8, kRingCl, kRingClThreads>::kElems
+                                 : RingCl<7, 7, kRingCl, kRingClThreads>::kElems;
+constexpr int kRingClSmem = (kRingClElems + 512) * (int)sizeof(float2);
+constexpr int kRingCl8Smem = (RingCl<8, 8, kRingCl8, kRingClThreads>::kElems + 512) * (int)sizeof(float2);
+
+// The first thing a cluster does is wait for its wave from HBM with nothing to overlap it with: pull the wave of
+// the cluster that will run here one generation later into L2 now (one 128-byte line per thread).
+template <int CL>
+__device__ __forceinline__ void prefetch_next_wave(const PrepParams& p, int u, int n_utts, int ahead_by) {
+    const int ahead = u + ahead_by;
+    if (ahead >= n_utts) return;
+    const UttDesc nx = p.utts[ahead];
+    const int esz = p.wave_dtype == F2_DT_I16 ? 2 : (p.wave_dtype == F2_DT_F32 ? 4 : 8);
+    const char* base = reinterpret_cast<const char*>(p.wave) + nx.wave_off * esz;
+    const long long bytes = (long long)nx.n * esz;
+    for (long long o = ((long long)(blockIdx.x % CL) * kRingClThreads + threadIdx.x) * 128; o < bytes;
+         o += (long long)CL * kRingClThreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+}
 
 __global__ void __cluster_dims__(kRingCl, 1, 1) __launch_bounds__(kRingClThreads, F2_RING_CTAS) ring_cluster_kernel(PrepParams p) {
     extern __shared__ float2 s_fft[];
     const int u = blockIdx.x / kRingCl, n_utts = gridDim.x / kRingCl;
     const UttDesc ut = p.utts[u];
-    {
-        // The first thing a cluster does is wait for its wave from HBM with nothing to overlap it with: pull the
-        // wave of the cluster that will run here one generation later into L2 now (one 128-byte line per thread).
-        const int ahead = u + kRingAhead;
-        if (ahead < n_utts) {
-            const UttDesc nx = p.utts[ahead];
-            const int esz = p.wave_dtype == F2_DT_I16 ? 2 : (p.wave_dtype == F2_DT_F32 ? 4 : 8);
-            const char* base = reinterpret_cast<const char*>(p.wave) + nx.wave_off * esz;
-            const long long bytes = (long long)nx.n * esz;
-            for (long long o = ((long long)(blockIdx.x % kRingCl) * kRingClThreads + threadIdx.x) * 128; o < bytes;
-                 o += (long long)kRingCl * kRingClThreads * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
-        }
-    }
-    if (ut.log2N2 == 16) ring_cluster_body<8, kRingCl, kRingClThreads>(p, ut, s_fft);
-    else if (ut.log2N2 == 15) ring_cluster_body<7, kRingCl, kRingClThreads>(p, ut, s_fft);
+    prefetch_next_wave<kRingCl>(p, u, n_utts, kRingAhead);
+    if (ut.log2N2 == 16) ring_cluster_body<7, 8, kRingCl, kRingClThreads>(p, ut, s_fft);
+    else if (ut.log2N2 == 15) ring_cluster_body<7, 7, kRingCl, kRingClThreads>(p, ut, s_fft);
+}
+
+// rings of 131072 samples (utterances of 4.1 ... 8.2 s): M = 256 x 256 packed points, a cluster of 8 CTAs
+__global__ void __cluster_dims__(kRingCl8, 1, 1) __launch_bounds__(kRingClThreads, F2_RING_CTAS) ring_cluster8_kernel(PrepParams p) {
+    extern __shared__ float2 s_fft[];
+    const int u = blockIdx.x / kRingCl8, n_utts = gridDim.x / kRingCl8;
+    const UttDesc ut = p.utts[u];
+    if (ut.log2N2 != 17) return;
+    prefetch_next_wave<kRingCl8>(p, u, n_utts, kRingAhead8);
+    ring_cluster_body<8, 8, kRingCl8, kRingClThreads>(p, ut, s_fft);
 }
 
 // One injection table per (device, ring size), built on first use and kept for the life of the process
@@ -989,7 +1022,7 @@ bool ring_cluster_enabled() {
 cudaError_t launch_prep(const PrepParams& p_in, const HostPrepInfo& h, cudaStream_t stream) {
     if (h.n_utts <= 0) return cudaSuccess;
     PrepParams p = p_in;
-    p.cluster = ring_cluster_enabled() && p.hilbert && h.min_log2N2 <= 16 && h.max_log2N2 >= 15;
+    p.cluster = ring_cluster_enabled() && p.hilbert && h.min_log2N2 <= 17 && h.max_log2N2 >= 15;
     if (h.max_log2N2 - 1 > 2 * kTwLog) return cudaErrorInvalidValue;
     // per device: the attribute belongs to the current device's copy of the function
     static bool attr_done[64] = {false};
@@ -1004,6 +1037,7 @@ cudaError_t launch_prep(const PrepParams& p_in, const HostPrepInfo& h, cudaStrea
         cudaFuncSetAttribute(fft_rows_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fft_cols_fast_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(ring_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingClSmem);
+        cudaFuncSetAttribute(ring_cluster8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingCl8Smem);
         if (dev < 64) attr_done[dev] = true;
     }
     const int maxN2 = 1 << h.max_log2N2;
@@ -1039,7 +1073,8 @@ cudaError_t launch_prep(const PrepParams& p_in, const HostPrepInfo& h, cudaStrea
     float* B = p.bufB;
     // whole transform in one cluster kernel for the corpus sizes (its utterances are skipped by everything below
     // except the G table)
-    if (p.cluster) ring_cluster_kernel<<<kRingCl * h.n_utts, kRingClThreads, kRingClSmem, stream>>>(p);
+    if (p.cluster && h.min_log2N2 <= 16) ring_cluster_kernel<<<kRingCl * h.n_utts, kRingClThreads, kRingClSmem, stream>>>(p);
+    if (p.cluster && h.max_log2N2 >= 17) ring_cluster8_kernel<<<kRingCl8 * h.n_utts, kRingClThreads, kRingCl8Smem, stream>>>(p);
     // forward
     if (fast) fft_cols_fast_kernel<false, true><<<g_fast, kFftThreads, 0, stream>>>(p, A);
     if (fast) fft_rows_fast_kernel<false, false><<<g_fast, kFftThreads, 0, stream>>>(p, A, B);
@@ -1047,7 +1082,7 @@ cudaError_t launch_prep(const PrepParams& p_in, const HostPrepInfo& h, cudaStrea
     if (two && slow2) fft_rows_kernel<false, false, false><<<g_rows, kFftThreads, smem, stream>>>(p, A, B);
     if (one) fft_rows_kernel<false, true, false><<<g_rows, kFftThreads, smem, stream>>>(p, nullptr, B);
     // Hilbert multiplier in place on B; the injection kernel goes to A (free from here on)
-    const bool all_cluster = p.cluster && h.min_log2N2 >= 15 && h.max_log2N2 <= 16;
+    const bool all_cluster = p.cluster && h.min_log2N2 >= 15 && h.max_log2N2 <= 17;
     if (!all_cluster || (p.G && h.private_g > 0)) hilbert_mask_kernel<<<g_ew, 256, 0, stream>>>(p.utts, B, p.G, p.cluster);
     // inverse, last pass writes the (x, xi) ring
     if (fast) fft_cols_fast_kernel<true, false><<<g_fast, kFftThreads, 0, stream>>>(p, B);

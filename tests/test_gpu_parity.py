@@ -598,12 +598,12 @@ def test_corpus_pipeline_input_forms_out_argument_and_fallthrough(gpu, monkeypat
 
 
 def test_one_kernel_ring_transform_sizes(gpu, oracle):
-    """The cluster kernel that transforms rings of 32768 and 65536 samples (every corpus utterance) in
+    """The cluster kernels that transform rings of 32768, 65536 (every corpus utterance) and 131072 samples in
     distributed shared memory: Im(paddedHilbert) of rows on both sides of its size range against the float64
     oracle (EnvelopeExtraction.py:20-36), including the sizes next to it that take the multi-pass kernels."""
     api, engine, filters, torch = gpu
     rng = np.random.default_rng(21)
-    for n in (16384, 16385, 20001, 32768, 32769, 47001, 65535, 65536, 65537):
+    for n in (16384, 16385, 20001, 32768, 32769, 47001, 65535, 65536, 65537, 100003, 131072, 131073):
         m = rng.normal(0.0, 3000.0, (3, n))
         got = api.hilbert_imag_rows(m)
         for r in range(3):

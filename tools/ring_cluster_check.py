@@ -10,7 +10,7 @@ def errors():
     from scipy.signal import hilbert
     from f2cnn_b200 import api
     rng = np.random.default_rng(7)
-    for n in (20000, 32768, 32769, 47001, 65535, 65536):
+    for n in (20000, 32768, 32769, 47001, 65535, 65536, 65537, 100003, 131072):
         m = rng.normal(0, 3000, (6, n))
         N2 = 1 << int(np.ceil(np.log2(n)))
         want = np.imag(hilbert(np.concatenate([m, np.zeros((6, N2 - n))], axis=1), axis=1))[:, :n]
@@ -23,6 +23,8 @@ def timing():
     from f2cnn_b200.gammatone import filters
     coefs = filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, 100))
     lengths = synth.corpus_lengths(4620, seed=1)
+    if os.environ.get("RING_CHECK_LONG"):   # a corpus of 4.1 ... 8.2 s utterances: rings of 131072 samples
+        lengths = synth.corpus_lengths(2310, 65537, 131072, seed=1)
     flat = torch.from_numpy(synth.corpus_waves_i16(lengths, seed=1)[0]).cuda()
     plan = engine.plan_for(coefs)
     batch = plan.batch(lengths, step=160, phase=0)
@@ -37,6 +39,7 @@ def timing():
     total, fused = t0.elapsed_time(t1), ev[0].elapsed_ms(ev[1])
     sums = torch.stack([out["dec"][int(a):int(b)].double().sum() for a, b in zip(batch.frame_offsets[:-1], batch.frame_offsets[1:])]).cpu().numpy()
     np.save("gpurun_out/ring_sums_%s.npy" % os.environ.get("F2CNN_B200_RING_CLUSTER", "1"), sums)
+    np.save("gpurun_out/ring_lengths.npy", lengths)
     print("cluster=%s  step %.3f ms = pre-pass %.3f + fused %.3f   checksum %.9e" % (
         os.environ.get("F2CNN_B200_RING_CLUSTER", "1"), total, total - fused, fused, float(out["dec"].double().sum())), flush=True)
 
@@ -49,8 +52,7 @@ if __name__ == "__main__":
         for v in ("1", "0"):
             subprocess.run([sys.executable, __file__, "timing"], env=dict(os.environ, F2CNN_B200_RING_CLUSTER=v))
         a, b = np.load("gpurun_out/ring_sums_1.npy"), np.load("gpurun_out/ring_sums_0.npy")
-        from f2cnn_b200 import synth
-        lengths = synth.corpus_lengths(4620, seed=1)
+        lengths = np.load("gpurun_out/ring_lengths.npy")
         rel = np.abs(a - b) / np.abs(b)
         bad = np.nonzero(rel > 1e-6)[0]
         print("per-utterance checksums: max rel diff %.2e, %d utterances above 1e-6" % (rel.max(), bad.size))
