@@ -531,10 +531,23 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
                 }
             }
         }
-        // longest first: the hardware dispatches CTAs in index order, so the tail is short items (the
-        // sort is stable: neighbours stay neighbours)
-        std::stable_sort(out.begin(), out.end(), [](const f2::Item& a, const f2::Item& c) {
-            return (a.t1 - a.t0) > (c.t1 - c.t0);
+        // Most expensive first: the hardware dispatches CTAs in index order, so the tail of the launch is made
+        // of its cheapest items.  Cost = (samples + the group's warm-up, which runs as scalar code at ~0.6 of a
+        // sample's price) x the group's section form (a direct-form group runs a sample in kDirectCost of a
+        // delta-form group's time): 38.8 -> 38.3 ms on the corpus against sorting by length alone.  The sort is
+        // stable, so equal items stay in utterance order.
+        std::vector<double> gcost((size_t)cblocks), gwarm((size_t)cblocks);
+        for (int cb = 0; cb < cblocks; ++cb) {
+            const size_t c0 = (size_t)cb * 32;
+            const float wscale = plan->h_chan[(size_t)f2::P_WSCALE * plan->c_pad + c0];
+            gcost[(size_t)cb] = plan->h_chan[(size_t)f2::P_FORM * plan->c_pad + c0] >= kDirectMinCyEnv ? kDirectCost : 1.0;
+            gwarm[(size_t)cb] = 0.6 * (f2::group_warmup(plan->w_imag, wscale) + f2::group_warmup(plan->w_edge, wscale));
+        }
+        const bool whole_utterances = seg >= ((long long)1 << 40);   // time chunks are cut to equal cost already
+        std::stable_sort(out.begin(), out.end(), [&](const f2::Item& a, const f2::Item& c) {
+            if (!whole_utterances) return (a.t1 - a.t0) > (c.t1 - c.t0);
+            return ((a.t1 - a.t0) + gwarm[(size_t)a.cblock]) * gcost[(size_t)a.cblock] >
+                   ((c.t1 - c.t0) + gwarm[(size_t)c.cblock]) * gcost[(size_t)c.cblock];
         });
         return out;
     };
