@@ -11,11 +11,11 @@ co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, 100))
 plan = engine.plan_for(co)
 lengths_all = synth.corpus_lengths(4620, 32000, 64000, seed=1)
 flat_all, offs = synth.corpus_waves_i16(lengths_all, seed=1)
-for world in (1, 2, 4, 8, 16, 32, 64):
+for world in [int(w) for w in os.environ.get('SHARD_WORLDS', '1,2,4,8,16,32,64').split(',')]:
     idx = engine.shard_utterances(lengths_all, world)[0]
     lengths = lengths_all[idx]
     wave = torch.from_numpy(np.concatenate([flat_all[offs[u]:offs[u + 1]] for u in idx])).cuda()
-    for target in (1, 0):
+    for target in ((1,) if os.environ.get('SHARD_WHOLE_ONLY') else (1, 0)):
         b = plan.batch(lengths, target_items=target)
         dec = torch.empty((b.total_frames, 128), dtype=torch.float32, device="cuda")
         ev = [(engine.DeviceEvent(), engine.DeviceEvent()) for _ in range(5)]
