@@ -112,6 +112,29 @@ def test_no_cpu_fallback_without_cuda():
         filters.erb_filterbank(np.zeros(100, dtype=np.int16), co)
 
 
+def test_host_memory_entry_points_without_a_device():
+    """f2_host_alloc / f2_host_free work anywhere; f2_host_pin needs CUDA and says so instead of crashing,
+    and the new frames API fails as loudly as the rest of the product path."""
+    import ctypes
+    import torch
+    from f2cnn_b200 import _native, api
+    from f2cnn_b200.gammatone import filters
+    L = _native.lib()
+    ptr = ctypes.c_void_p()
+    assert L.f2_host_alloc(1 << 22, ctypes.byref(ptr)) == 0 and ptr.value
+    np.frombuffer((ctypes.c_char * (1 << 22)).from_address(ptr.value), dtype=np.uint8)[::4096] = 7   # writable
+    if not torch.cuda.is_available():
+        assert L.f2_host_pin(ptr, 1 << 22) != 0
+        assert b"f2_host_pin" in L.f2_last_error()
+        co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 8, 100))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            api.features_to_frames([np.zeros(4000, dtype=np.int16)], co)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            api.gammatonegram(np.zeros(4000, dtype=np.int16), co, 16)
+    assert L.f2_host_pin(None, 0) != 0
+    assert L.f2_host_free(ptr, 1 << 22) == 0
+
+
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under f2cnn_b200/ may reference it."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "f2cnn_b200")):
