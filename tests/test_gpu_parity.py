@@ -705,3 +705,36 @@ def test_frame_windows_are_views_of_the_decimated_frames(gpu, monkeypatch):
             assert np.array_equal(h.windows(j), want[first_row[u]:first_row[u + 1]]), u
     with pytest.raises(IndexError):
         api.features_to_frames(waves, co, True, 50, counts=nwin + 3)
+
+
+def test_multi_pass_prepass_agrees_with_the_cluster_kernels(gpu):
+    """F2CNN_B200_RING_CLUSTER=0 sends rings of 32768 / 65536 / 131072 samples through the five-kernel
+    pre-pass the cluster kernels replaced (kept as their cross-check): a child process computes the same
+    decimated envelopes that way; the two agree far inside the tolerance (different FFT factorisations)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    api, engine, filters, torch = gpu
+    from f2cnn_b200 import synth
+    lens = [20000, 40000, 65536, 70001]
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from f2cnn_b200 import engine, synth\n"
+        "from f2cnn_b200.gammatone import filters\n"
+        "co = filters.make_erb_filters(16000, filters.centre_freqs(16000, 128, 100))\n"
+        "lens = %r\n"
+        "flat = torch.from_numpy(np.concatenate([synth.white_noise_i16(n, seed=900 + i) for i, n in enumerate(lens)])).cuda()\n"
+        "dec = engine.plan_for(co).batch(lens, target_items=1).run(flat, lpf=True, cutoff=50, dec=True)['dec']\n"
+        "np.save(sys.argv[1], dec.cpu().numpy())\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), lens))
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for flag in ("1", "0"):
+            path = os.path.join(d, "dec%s.npy" % flag)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, F2CNN_B200_RING_CLUSTER=flag),
+                           timeout=300)
+            out[flag] = np.load(path).astype(np.float64)
+    assert out["1"].shape == out["0"].shape and not np.array_equal(out["1"], out["0"])   # really two code paths
+    rms = np.sqrt(np.mean(out["0"] ** 2, axis=0))
+    assert (np.max(np.abs(out["1"] - out["0"]), axis=0) / rms).max() <= 2e-5
