@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 FS, C, LOW, CUTOFF, RADIUS, STEP = 16000, 128, 100, 50, 5, 160
 N_UTTS, LEN_LO, LEN_HI = 4620, 32000, 64000
 FLOP_PER_CS = 80.0  # 40 FP32 FMA per channel-sample: filterbank + envelope + LPF
-TRAFFIC_1GPU = 13.040e9  # bytes per fused_kernel launch (window-store mode): 5.59 GB read + 7.45 GB written, profiles/r02z_ncu_final.md
+TRAFFIC_1GPU = 11.520e9  # bytes per fused_kernel launch (window-store mode): 4.08 GB read + 7.44 GB written (ncu)
 KERNELS_PER_STEP = 2  # ring_cluster_kernel (whole pre-pass of the corpus sizes), fused_kernel (stores the windows)
 
 

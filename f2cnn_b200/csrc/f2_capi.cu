@@ -533,11 +533,13 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
                 }
             }
         }
-        // Most expensive first: the hardware dispatches CTAs in index order, so the tail of the launch is made
-        // of its cheapest items.  Cost = (samples + the group's warm-up, which runs as scalar code at ~0.6 of a
+        // Longest first -- the hardware dispatches CTAs in index order, and the channel groups of an utterance stay
+        // neighbours, so they share its ring tiles in L2 -- except for the last two waves of the launch, which go
+        // most expensive first: cost = (samples + the group's warm-up, which runs as scalar code at ~0.6 of a
         // sample's price) x the group's section form (a direct-form group runs a sample in kDirectCost of a
-        // delta-form group's time): 38.8 -> 38.3 ms on the corpus against sorting by length alone.  The sort is
-        // stable, so equal items stay in utterance order.
+        // delta-form group's time), so that the launch does not end on slow delta-form items.  On the corpus:
+        // 38.85 ms by length alone, 38.43 ms with the two-wave tail (4.3 GB read), 38.34 ms with the whole list by
+        // cost (5.6 GB read: the delta-form group of an utterance then runs far ahead of its siblings).
         std::vector<double> gcost((size_t)cblocks), gwarm((size_t)cblocks);
         for (int cb = 0; cb < cblocks; ++cb) {
             const size_t c0 = (size_t)cb * 32;
@@ -545,12 +547,19 @@ int f2_batch_create(f2_plan* plan, const int64_t* lengths, int n_utts, int step,
             gcost[(size_t)cb] = plan->h_chan[(size_t)f2::P_FORM * plan->c_pad + c0] >= kDirectMinCyEnv ? kDirectCost : 1.0;
             gwarm[(size_t)cb] = 0.6 * (f2::group_warmup(plan->w_imag, wscale) + f2::group_warmup(plan->w_edge, wscale));
         }
-        const bool whole_utterances = seg >= ((long long)1 << 40);   // time chunks are cut to equal cost already
-        std::stable_sort(out.begin(), out.end(), [&](const f2::Item& a, const f2::Item& c) {
-            if (!whole_utterances) return (a.t1 - a.t0) > (c.t1 - c.t0);
+        const bool whole_utterances = seg >= ((long long)1 << 40);
+        auto by_length = [](const f2::Item& a, const f2::Item& c) { return (a.t1 - a.t0) > (c.t1 - c.t0); };
+        auto by_cost = [&](const f2::Item& a, const f2::Item& c) {
             return ((a.t1 - a.t0) + gwarm[(size_t)a.cblock]) * gcost[(size_t)a.cblock] >
                    ((c.t1 - c.t0) + gwarm[(size_t)c.cblock]) * gcost[(size_t)c.cblock];
-        });
+        };
+        std::stable_sort(out.begin(), out.end(), by_length);
+        if (whole_utterances) {   // time chunks are cut to equal cost already
+            const char* tail_env = getenv("F2CNN_B200_TAIL_ITEMS");   // development knob
+            const size_t want = tail_env ? (size_t)atoll(tail_env) : (size_t)sm_count * 16 * 2;
+            const size_t tail = std::min(out.size(), want);
+            std::stable_sort(out.end() - (long)tail, out.end(), by_cost);
+        }
         // One wave or less (a shard of the corpus on one of eight GPUs): the CTAs are handed to the SMs round
         // after round, so with items in descending order the first SMs collect the most expensive item of every
         // round.  Every other round reversed ("snake"), all SMs get about the same sum: 5.92 -> 5.82 ms on a
