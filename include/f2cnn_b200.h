@@ -105,7 +105,9 @@ typedef struct f2_run_args {
     void* env;        /* out, nullable: ExtractEnvelopeFromMatrix result, same layout      */
     int env_dtype;
     float* env_t;     /* out, nullable: envelope time-major [sum n][C] float32             */
-    float* dec;       /* out, nullable: decimated envelope frames [total_frames][C] float32 */
+    float* dec;       /* out, nullable: decimated envelope frames [total_frames][C] float32.  The one output that may
+                       * also be page-locked HOST memory the device can address under the same pointer (f2_host_pin):
+                       * the kernel then stores the frames over PCIe as it produces them (the corpus pipeline) */
     void* ev_fused_start; /* nullable cudaEvent_t recorded on `stream` right before ...     */
     void* ev_fused_stop;  /* ... and right after the fused kernel (for roofline timing)     */
     /* Windows on the decimated grid written by the fused kernel itself (the rows GenerateInputData
