@@ -209,3 +209,35 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_frame_windows_views_getitem_and_materialize_on_the_host():
+    """api.FrameWindows is host logic over a frames array: utterance blocks as strided views, global rows,
+    and materialize() through the library's placement pool -- against plain numpy indexing."""
+    from f2cnn_b200 import api, engine
+    rng = np.random.default_rng(11)
+    n_frames = np.array([40, 12, 11, 0, 25], dtype=np.int64)          # 12 frames: 2 windows; 11: exactly 1
+    counts = np.maximum(n_frames - 10, 0)
+    counts[1] = 1                                                       # fewer windows than the frames allow
+    frame_offsets = np.concatenate([[0], np.cumsum(n_frames)]).astype(np.int64)
+    frames = rng.standard_normal((int(frame_offsets[-1]), 128)).astype(np.float32)
+    fw = api.FrameWindows(frames, frame_offsets, counts, 11, np.arange(5), engine.Placer(3))
+    want = np.concatenate([np.stack([frames[frame_offsets[u] + k:frame_offsets[u] + k + 11] for k in range(int(c))])
+                           for u, c in enumerate(counts) if c > 0])
+    assert len(fw) == want.shape[0] == int(counts.sum())
+    row = 0
+    for u, c in enumerate(counts):
+        v = fw.windows(u)
+        assert v.shape == (c, 11, 128) and np.array_equal(v, want[row:row + int(c)])
+        assert c == 0 or np.shares_memory(v, frames)
+        row += int(c)
+    for r in list(range(len(fw))) + [-1, -len(fw)]:
+        assert np.array_equal(fw[r], want[r])
+    for bad in (len(fw), -len(fw) - 1):
+        with pytest.raises(IndexError):
+            fw[bad]
+    assert np.array_equal(fw.materialize(), want)
+    out = np.zeros_like(want)
+    assert fw.materialize(out) is out and np.array_equal(out, want)
+    with pytest.raises(ValueError):
+        fw.windows(0)[0, 0, 0] = 1.0                                    # views are read-only
